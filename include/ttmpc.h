@@ -1,0 +1,241 @@
+/*
+ * ttmpc.h -- C-ABI of the B200-native batched NMPC planner + DQN companion.
+ *
+ * This is the drop-in boundary for ONE path of Woodenonez/TrajTrack-MPCnDQN-RLBoost:
+ * the call that the reference makes into its OpEn-generated (Rust, PyO3) solver
+ *
+ *     solution = self.solver.run(parameters, initial_guess)
+ *         -- src/mpc_traj_tracker/trajectory_generator.py:284
+ *     class Solver: def run(self, p, initial_guess, initial_lagrange_multipliers,
+ *                           initial_penalty) -> SolverStatus
+ *         -- src/mpc_traj_tracker/trajectory_generator.py:27-29
+ *
+ * and, for the DQN-boosted loop, the observation + policy call
+ *
+ *     obsv['external'] = SectorAndRayObservation.external_obs()
+ *         -- src/pkg_dqn/environment/components/ext_obsv_sector_and_ray.py:33-83
+ *     action_index, _ = model.predict(obsv, deterministic=True)
+ *         -- src/main.py:148 (SB3 DQN MultiInputPolicy, net_arch [16,16])
+ *
+ * Everything is plain pointers and sizes.  No torch types, no C++ types.
+ * Pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ * All entry points return 0 on success, a negative ttmpc error code otherwise;
+ * ttmpc_last_error() gives a human-readable string for the calling thread.
+ *
+ * The packed parameter vector p of one scene is laid out exactly as the
+ * reference assembles it (trajectory_generator.py:251-254, mpc_generator.py:175-184):
+ *
+ *   s     [2*ns+nu]              x y theta | x_goal y_goal theta_goal | v_init w_init
+ *   q     [nq = 10]              qpos qvel qtheta rv rw qN qthetaN qrpd acc_pen wacc_pen
+ *   r     [ns*N + N]             (x y theta) * N reference states, then N speed refs
+ *   c     [ns*N*Nother]          predicted states of other robots, robot-major
+ *   o_s   [Nstcobs*nstcobs]      per obstacle: b[ne] a0[ne] a1[ne]   (ne = nstcobs/3)
+ *   o_d   [Ndynobs*ndynobs*N]    per obstacle, per step: cx cy rx ry angle alpha
+ *   q_stc [N]                    static-obstacle weights (unused by the cost, kept)
+ *   q_dyn [N]                    dynamic-obstacle soft weights
+ *
+ * Batches are scene-major: p[scene][np], u[scene][nu*N], y[scene][2*N].
+ */
+#ifndef TTMPC_H
+#define TTMPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTMPC_VERSION 100
+
+/* exit_status codes; names are the strings the OpEn python binding returns
+ * (format!("{:?}", ExitStatus)), which the reference matches against
+ * config.bad_exit_codes (config/mpc_default.yaml:58).  */
+enum {
+  TTMPC_CONVERGED = 0,                 /* "Converged"              */
+  TTMPC_NOT_CONVERGED_ITERATIONS = 1,  /* "NotConvergedIterations" */
+  TTMPC_NOT_CONVERGED_OUT_OF_TIME = 2, /* "NotConvergedOutOfTime"  */
+  TTMPC_NOT_FINITE = 3                 /* SolverError::NotFiniteComputation: the
+                                          binding returns None -> reference raises */
+};
+
+enum {
+  TTMPC_OK = 0,
+  TTMPC_ERR_BAD_CONFIG = -1,
+  TTMPC_ERR_BAD_ARG = -2,
+  TTMPC_ERR_CUDA = -3,
+  TTMPC_ERR_UNSUPPORTED = -4
+};
+
+/* Problem + solver configuration.
+ * Problem fields mirror config/mpc_default.yaml; solver fields mirror
+ * opengen.config.SolverConfiguration as used at mpc_generator.py:268-276
+ * (initial_penalty 10, everything else opengen 0.7.1 defaults).          */
+typedef struct ttmpc_config {
+  /* dimensions */
+  int N_hor;    /* horizon, 1..32 (one lane per step)                  */
+  int nu;       /* must be 2 (v, omega)                                */
+  int ns;       /* must be 3 (x, y, theta)                             */
+  int nq;       /* must be 10                                          */
+  int Nother;   /* other-robot slots                                   */
+  int Nstcobs;  /* static obstacle slots                               */
+  int nstcobs;  /* doubles per static obstacle = 3*edges, edges<=8     */
+  int Ndynobs;  /* dynamic obstacle slots                              */
+  int ndynobs;  /* must be 6                                           */
+  int _pad0;
+  /* model */
+  double ts;
+  double vehicle_width;  /* fleet safe distance                         */
+  double social_margin;  /* soft-ellipse inflation                      */
+  double lin_vel_min, lin_vel_max, ang_vel_max; /* box on u              */
+  double lin_acc_min, lin_acc_max, ang_acc_max; /* set C of the ALM map  */
+  /* solver (OpEn) */
+  double tolerance;              /* epsilon, 1e-4                        */
+  double initial_tolerance;      /* initial inner AKKT tolerance, 1e-4   */
+  double delta_tolerance;        /* constraints tolerance, 1e-4          */
+  double initial_penalty;        /* 10 (mpc_generator.py:269)            */
+  double penalty_update_factor;  /* 5                                    */
+  double inner_tolerance_update_factor; /* 0.1                           */
+  double sufficient_decrease_coeff;     /* 0.1                           */
+  int lbfgs_memory;              /* 10, max 16                           */
+  int max_inner_iterations;      /* 500                                  */
+  int max_outer_iterations;      /* 10                                   */
+  int _pad1;
+} ttmpc_config;
+
+/* Fill cfg with config/mpc_default.yaml + opengen defaults. */
+void ttmpc_default_config(ttmpc_config *cfg);
+/* Number of doubles in one packed parameter vector / decision vector / F1 / F2. */
+int ttmpc_num_params(const ttmpc_config *cfg);
+int ttmpc_num_decision(const ttmpc_config *cfg);
+int ttmpc_num_alm(const ttmpc_config *cfg);     /* n1 = 2*N_hor */
+int ttmpc_num_penalty(const ttmpc_config *cfg); /* n2 = Ndynobs */
+const char *ttmpc_last_error(void);
+const char *ttmpc_exit_status_name(int code);
+int ttmpc_version(void);
+
+/* Per-scene outputs of a batched solve.  Any pointer may be NULL (skipped)
+ * except u.  Mirrors the fields of OpEn's python OptimizerSolution that the
+ * reference reads (trajectory_generator.py:286-289) plus the diagnostics.  */
+typedef struct ttmpc_result {
+  double *u;            /* [n][nu*N]  in: initial guess (see use_u0), out: solution */
+  double *cost;         /* [n]  f(u*) (psi with c = 0)                              */
+  int *exit_status;     /* [n]                                                      */
+  int *outer_iters;     /* [n]                                                      */
+  int *inner_iters;     /* [n]                                                      */
+  double *last_fpr;     /* [n]  last_problem_norm_fpr                               */
+  double *f1_infeas;    /* [n]  delta_y_norm / c                                    */
+  double *f2_norm;      /* [n]                                                      */
+  double *penalty;      /* [n]  final c                                             */
+  double *y;            /* [n][2*N] in: initial multipliers (see use_y0), out: final */
+  double *pred_states;  /* [n][N][ns] rollout of u* from p.s (trajectory_generator.py:296-301) */
+  long long *evals;     /* [n][2] number of (cost-only, cost+gradient) evaluations  */
+} ttmpc_result;
+
+/* ------------------------------------------------------------------------
+ * Batched NMPC solve, device-resident.  All pointers in res and d_p are
+ * device pointers.  Asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   use_u0 = 0: initial guess is all-zero, like solver.run(p) with
+ *               initial_guess=None; res->u is output only.
+ *   use_y0 = 0: multipliers start at zero.  (The reference's Solver object
+ *               keeps them between run() calls; the host mirror does that.)
+ *   d_c0      : optional per-scene initial penalty (NULL -> cfg value).
+ * ------------------------------------------------------------------------ */
+int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes,
+                             const double *d_p, int use_u0, int use_y0,
+                             const double *d_c0, const ttmpc_result *res,
+                             void *stream);
+
+/* Same call with HOST buffers: stages p/u/y through pinned memory, launches,
+ * copies results back, synchronises.  This is what the python Solver.run
+ * mirror and the `e2e` bench leg use.                                     */
+int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n_scenes,
+                           const double *h_p, int use_u0, int use_y0,
+                           const double *h_c0, const ttmpc_result *res);
+
+/* Evaluate the problem functions on device for a batch (testing / parity):
+ * f, F1 [n][2N], F2 [n][Ndynobs], and psi/grad psi at xi = (c, y).
+ * Any output may be NULL.  d_c [n], d_y [n][2N] may be NULL (c=0, y=0).   */
+int ttmpc_eval_batch_device(const ttmpc_config *cfg, int n_scenes,
+                            const double *d_p, const double *d_u,
+                            const double *d_c, const double *d_y, double *d_f,
+                            double *d_F1, double *d_F2, double *d_psi,
+                            double *d_grad, void *stream);
+int ttmpc_eval_batch_host(const ttmpc_config *cfg, int n_scenes,
+                          const double *h_p, const double *h_u,
+                          const double *h_c, const double *h_y, double *h_f,
+                          double *h_F1, double *h_F2, double *h_psi,
+                          double *h_grad);
+
+/* ------------------------------------------------------------------------
+ * DQN companion: sector+ray ("lidar") observation against the obstacle set,
+ * then Q-network inference and argmax, one environment per warp.
+ *
+ * Geometry of one env (all fp64, world frame, already padded as the reference
+ * pads them: obstacle.py:158-163,248-254):
+ *   polygons: n_poly closed rings, ring i has poly_nv[i] vertices stored at
+ *             poly_xy[poly_off[i] .. ], (x,y) pairs.  is_solid[i] != 0 for an
+ *             obstacle (filled Polygon), 0 for the boundary ring (LineString).
+ * Batched layout: fixed capacity per env: max_poly rings, max_vert vertices.
+ * ------------------------------------------------------------------------ */
+typedef struct ttdqn_scene_layout {
+  int num_segments; /* 8 (rays_reward1.py:20)                              */
+  int max_poly;     /* ring slots per env                                  */
+  int max_vert;     /* vertex slots per env (sum over rings)               */
+  int n_internal;   /* 14 internal observation entries                     */
+  int use_memory;   /* 1: external obs = [seg, ray, old_seg, old_ray]      */
+  int _pad;
+  double ray_length;   /* L = 1000 (ext_obsv_sector_and_ray.py:34)         */
+  double max_distance; /* normalize_distance max_distance = 10 (utils.py:10) */
+} ttdqn_scene_layout;
+
+/* Q-network weights, fp32 row-major [out][in] like torch.nn.Linear.
+ * Input is concat(external[4*num_segments or 2*num_segments], internal[n_internal])
+ * (SB3 CombinedExtractor concatenates Dict keys in sorted order:
+ *  'external' then 'internal').                                           */
+typedef struct ttdqn_qnet {
+  int n_in, n_h1, n_h2, n_out; /* 46, 16, 16, 9 */
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+} ttdqn_qnet;
+
+void ttdqn_default_layout(ttdqn_scene_layout *lay);
+
+/* Device-resident batched observe + act.
+ *   d_agent    [n][3]   x y theta (fp64)
+ *   d_poly_xy  [n][max_vert][2], d_poly_off [n][max_poly+1] (prefix offsets),
+ *   d_is_solid [n][max_poly], d_n_poly [n]
+ *   d_internal [n][n_internal] fp32 internal observation
+ *   d_old_ext  [n][2*num_segments] fp32 in/out memory of previous (seg, ray) obs
+ *              (NULL when use_memory == 0)
+ * outputs (any may be NULL): d_ext [n][n_ext] fp32, d_q [n][n_out] fp32,
+ *   d_action [n] int32, d_seg_dist / d_ray_dist [n][num_segments] fp64 raw distances.
+ * qnet pointers are device pointers.                                      */
+int ttdqn_observe_act_device(const ttdqn_scene_layout *lay, const ttdqn_qnet *qnet,
+                             int n_envs, const double *d_agent,
+                             const double *d_poly_xy, const int *d_poly_off,
+                             const int *d_is_solid, const int *d_n_poly,
+                             const float *d_internal, float *d_old_ext,
+                             float *d_ext, float *d_q, int *d_action,
+                             double *d_seg_dist, double *d_ray_dist, void *stream);
+int ttdqn_observe_act_host(const ttdqn_scene_layout *lay, const ttdqn_qnet *qnet,
+                           int n_envs, const double *h_agent,
+                           const double *h_poly_xy, const int *h_poly_off,
+                           const int *h_is_solid, const int *h_n_poly,
+                           const float *h_internal, float *h_old_ext,
+                           float *h_ext, float *h_q, int *h_action,
+                           double *h_seg_dist, double *h_ray_dist);
+
+/* Cumulative device-side counters since the last reset: [0] cost-only
+ * evaluations, [1] cost+gradient evaluations, [2] dynamic-obstacle bodies that
+ * passed the bounding test, [3] PANOC iterations.  Synchronises the device.   */
+int ttmpc_read_stats(unsigned long long out[4], int reset);
+/* Launch geometry the solve kernel uses for n_scenes (reporting only). */
+int ttmpc_launch_info(const ttmpc_config *cfg, int n_scenes, int *grid, int *block,
+                      int *smem_bytes, int *blocks_per_sm, int *sm_count);
+
+/* FP64 FMA-pipe peak probe: runs a dependent-chain-free DFMA kernel on every
+ * SM and returns achieved TFLOP/s (used by bench.py as the roofline
+ * denominator for the FP64-bound solve kernel).                            */
+int ttmpc_measure_fp64_peak(double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTMPC_H */

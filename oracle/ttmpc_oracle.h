@@ -1,0 +1,79 @@
+/*
+ * ttmpc_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C fp64 restatement of the reference's NMPC path.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load this library.  The product (trajtrack_mpcndqn_rlboost_b200) never does.
+ *
+ * PARITY STATUS
+ *   problem functions (f, grad f, F1, F2): PINNED -- checked against the
+ *     reference's own MpcModule.build (src/mpc_traj_tracker/mpc/mpc_generator.py)
+ *     executed in-container with a torch-backed casadi shim
+ *     (tools/gen_golden_problem.py -> tests/golden/problem_*.npz).
+ *   PANOC / ALM / L-BFGS: PARITY UNPINNED -- the algorithm lives in the
+ *     third-party Rust crate `optimization_engine` (pulled by opengen==0.7.1,
+ *     requirements.txt:25; crate 0.7.x, lbfgs 0.2.x), absent from
+ *     /root/reference and not buildable here (no Rust).  Restated from the
+ *     published algorithm (Stella et al. 2017; Sopasakis et al. 2020) and the
+ *     crate's documented constants.
+ *   sector/ray observation: PARITY UNPINNED (shapely absent); Q-network: PINNED
+ *     against torch with the reference's Model/ray/best_model.zip weights.
+ */
+#ifndef TTMPC_ORACLE_H
+#define TTMPC_ORACLE_H
+#include "../include/ttmpc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ttmpc_oracle_status {
+  int exit_status;
+  int outer_iters;
+  int inner_iters;
+  double last_fpr;
+  double delta_y_norm;
+  double f2_norm;
+  double penalty;
+  double cost;
+  long long n_cost_evals;
+  long long n_grad_evals;
+} ttmpc_oracle_status;
+
+/* f(u;p), F1 [2N], F2 [Ndynobs].  Any output may be NULL. */
+void ttmpc_oracle_eval(const ttmpc_config *cfg, const double *u, const double *p,
+                       double *f, double *F1, double *F2);
+/* psi(u; xi=(c,y), p) and its gradient (hand-written adjoint). */
+double ttmpc_oracle_psi(const ttmpc_config *cfg, const double *u, const double *p,
+                        double c, const double *y);
+void ttmpc_oracle_psi_grad(const ttmpc_config *cfg, const double *u, const double *p,
+                           double c, const double *y, double *grad);
+/* One full OpEn-style solve.  u: in = initial guess, out = solution.
+ * y: in = initial Lagrange multipliers, out = final (len 2N).          */
+int ttmpc_oracle_solve(const ttmpc_config *cfg, const double *p, double *u,
+                       double *y, double c0, ttmpc_oracle_status *st);
+/* Batched convenience (sequential loop, or `threads` pthreads).
+ * Same per-scene arrays as ttmpc_result (host pointers).               */
+int ttmpc_oracle_solve_batch(const ttmpc_config *cfg, int n, const double *p,
+                             int use_u0, int use_y0, const double *c0,
+                             const ttmpc_result *res, int threads);
+/* Rollout of u from p.s: states [N][3] (trajectory_generator.py:296-301). */
+void ttmpc_oracle_rollout(const ttmpc_config *cfg, const double *u, const double *p,
+                          double *states);
+
+/* DQN companion oracle: one env. */
+void ttdqn_oracle_observe(const ttdqn_scene_layout *lay, const double *agent,
+                          const double *poly_xy, const int *poly_off,
+                          const int *is_solid, int n_poly, double *seg_dist,
+                          double *ray_dist);
+void ttdqn_oracle_observe_act(const ttdqn_scene_layout *lay, const ttdqn_qnet *qnet,
+                              int n_envs, const double *agent, const double *poly_xy,
+                              const int *poly_off, const int *is_solid,
+                              const int *n_poly, const float *internal,
+                              float *old_ext, float *ext, float *q, int *action,
+                              double *seg_dist, double *ray_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,123 @@
+"""ctypes binding of the CPU oracle (oracle/libttmpc_oracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+leg may import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from trajtrack_mpcndqn_rlboost_b200._lib import TtmpcConfig, TtmpcResult, TtdqnLayout, TtdqnQnet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_PATH = os.path.join(ROOT, "oracle", "libttmpc_oracle.so")
+
+
+class OracleStatus(C.Structure):
+    _fields_ = [("exit_status", C.c_int), ("outer_iters", C.c_int), ("inner_iters", C.c_int),
+                ("last_fpr", C.c_double), ("delta_y_norm", C.c_double), ("f2_norm", C.c_double),
+                ("penalty", C.c_double), ("cost", C.c_double),
+                ("n_cost_evals", C.c_longlong), ("n_grad_evals", C.c_longlong)]
+
+
+_lib = None
+
+
+def build():
+    src = [os.path.join(ROOT, "oracle", f) for f in ("ttmpc_oracle.c", "ttdqn_oracle.c")]
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", ORACLE_PATH,
+                           *src, "-lm", "-lpthread"])
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_PATH):
+            build()
+        lib = C.CDLL(ORACLE_PATH)
+        VP, I, D = C.c_void_p, C.c_int, C.c_double
+        CFG = C.POINTER(TtmpcConfig)
+        lib.ttmpc_oracle_eval.argtypes = [CFG, VP, VP, VP, VP, VP]
+        lib.ttmpc_oracle_psi.argtypes = [CFG, VP, VP, D, VP]
+        lib.ttmpc_oracle_psi.restype = D
+        lib.ttmpc_oracle_psi_grad.argtypes = [CFG, VP, VP, D, VP, VP]
+        lib.ttmpc_oracle_solve.argtypes = [CFG, VP, VP, VP, D, C.POINTER(OracleStatus)]
+        lib.ttmpc_oracle_solve_batch.argtypes = [CFG, I, VP, I, I, VP, C.POINTER(TtmpcResult), I]
+        lib.ttmpc_oracle_rollout.argtypes = [CFG, VP, VP, VP]
+        lib.ttdqn_oracle_observe_act.argtypes = [C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet), I] + [VP] * 12
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def evaluate(cfg, u, p):
+    lib = load()
+    N = cfg.N_hor
+    u = np.ascontiguousarray(u, np.float64); p = np.ascontiguousarray(p, np.float64)
+    f = np.zeros(1); F1 = np.zeros(2 * N); F2 = np.zeros(max(cfg.Ndynobs, 1))
+    lib.ttmpc_oracle_eval(C.byref(cfg), _p(u), _p(p), _p(f), _p(F1), _p(F2))
+    return float(f[0]), F1, F2[:cfg.Ndynobs]
+
+
+def psi(cfg, u, p, c, y=None):
+    lib = load()
+    u = np.ascontiguousarray(u, np.float64); p = np.ascontiguousarray(p, np.float64)
+    y = None if y is None else np.ascontiguousarray(y, np.float64)
+    return lib.ttmpc_oracle_psi(C.byref(cfg), _p(u), _p(p), float(c), _p(y))
+
+
+def psi_grad(cfg, u, p, c, y=None):
+    lib = load()
+    u = np.ascontiguousarray(u, np.float64); p = np.ascontiguousarray(p, np.float64)
+    y = None if y is None else np.ascontiguousarray(y, np.float64)
+    g = np.zeros(2 * cfg.N_hor)
+    lib.ttmpc_oracle_psi_grad(C.byref(cfg), _p(u), _p(p), float(c), _p(y), _p(g))
+    return g
+
+
+def solve_batch(cfg, p, u0=None, y0=None, c0=None, threads=1):
+    """Same outputs as BatchSolver.run (dict of numpy arrays)."""
+    lib = load()
+    p = np.ascontiguousarray(p, np.float64)
+    n, N = p.shape[0], cfg.N_hor
+    u = np.zeros((n, 2 * N)) if u0 is None else np.array(u0, np.float64, order="C").reshape(n, 2 * N)
+    y = np.zeros((n, 2 * N)) if y0 is None else np.array(y0, np.float64, order="C").reshape(n, 2 * N)
+    c0a = None if c0 is None else np.ascontiguousarray(np.broadcast_to(np.asarray(c0, np.float64), (n,)))
+    out = dict(cost=np.zeros(n), exit_status=np.zeros(n, np.int32), outer=np.zeros(n, np.int32),
+               inner=np.zeros(n, np.int32), fpr=np.zeros(n), f1=np.zeros(n), f2=np.zeros(n),
+               pen=np.zeros(n), pred=np.zeros((n, N, 3)), evals=np.zeros((n, 2), np.int64))
+    res = TtmpcResult(u=_p(u), cost=_p(out["cost"]), exit_status=_p(out["exit_status"]),
+                      outer_iters=_p(out["outer"]), inner_iters=_p(out["inner"]), last_fpr=_p(out["fpr"]),
+                      f1_infeas=_p(out["f1"]), f2_norm=_p(out["f2"]), penalty=_p(out["pen"]), y=_p(y),
+                      pred_states=_p(out["pred"]), evals=_p(out["evals"]))
+    lib.ttmpc_oracle_solve_batch(C.byref(cfg), n, _p(p), int(u0 is not None), int(y0 is not None),
+                                 _p(c0a), C.byref(res), int(threads))
+    out["u"] = u; out["y"] = y
+    return out
+
+
+def observe_act(lay, weights, agent, xy, off, sol, cnt, internal=None, old_ext=None):
+    lib = load()
+    n = len(agent)
+    ns = lay.num_segments
+    n_ext = (4 if lay.use_memory else 2) * ns
+    agent = np.ascontiguousarray(agent, np.float64)
+    internal = np.zeros((n, lay.n_internal), np.float32) if internal is None else \
+        np.ascontiguousarray(internal, np.float32)
+    old_ext = np.zeros((n, 2 * ns), np.float32) if old_ext is None else old_ext
+    ext = np.zeros((n, n_ext), np.float32)
+    q = np.zeros((n, weights.n_out), np.float32)
+    act = np.zeros(n, np.int32)
+    seg = np.zeros((n, ns)); ray = np.zeros((n, ns))
+    qs = weights.host_struct()
+    lib.ttdqn_oracle_observe_act(C.byref(lay), C.byref(qs), n, _p(agent), _p(xy), _p(off), _p(sol),
+                                 _p(cnt), _p(internal), _p(old_ext), _p(ext), _p(q), _p(act), _p(seg),
+                                 _p(ray))
+    return dict(ext=ext, q=q, action=act, seg=seg, ray=ray, old_ext=old_ext)

@@ -1,0 +1,13 @@
+"""trajtrack_mpcndqn_rlboost_b200 -- B200-native batched NMPC planner + DQN companion.
+
+Holds only what the hot path needs: csrc/ (sm_100a CUDA kernels + the C-ABI of
+include/ttmpc.h) and the host-side mirror of the reference's solver interface.
+"""
+from .mpc_config import Configurator, num_params, param_offsets  # noqa: F401
+from .solver import BatchSolver, Solver, OptimizerSolution, BatchSolution, EXIT_STATUS_NAMES  # noqa: F401
+from .planner import TrajectoryGenerator, InterfaceMpc  # noqa: F401
+from .motion_model import unicycle_model  # noqa: F401
+from . import scenes, dqn, geometry  # noqa: F401
+
+__all__ = ["Configurator", "BatchSolver", "Solver", "TrajectoryGenerator", "InterfaceMpc",
+           "unicycle_model", "scenes", "dqn", "geometry"]

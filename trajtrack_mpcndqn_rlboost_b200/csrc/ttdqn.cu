@@ -1,0 +1,380 @@
+// ttdqn.cu -- DQN companion kernel: sector+ray ("lidar") observation against the
+// obstacle set, Q-network inference and argmax, one environment per warp, so
+// the DQN-boosted action selection stays on the device next to the NMPC solve.
+//
+// Reference behaviour:
+//   SectorAndRayObservation.external_obs
+//     /root/reference/src/pkg_dqn/environment/components/ext_obsv_sector_and_ray.py:33-83
+//   normalize_distance           src/pkg_dqn/environment/components/utils.py:10-15
+//   model.predict(obsv, deterministic=True)   src/main.py:148
+//     (SB3 1.6.2 DQN MultiInputPolicy: concat(external, internal) -> 46-16-16-9 ReLU MLP -> argmax)
+//
+// Geometry: for sector triangle T with apex at the agent A, and a closed ring G,
+// the closest point of T^G to A lies on G's boundary whenever A is outside G, so
+// the sector distance is min over edges e of dist(A, e clipped to T); the ray
+// distance is the first hit along the centre ray.  A inside a solid ring gives 0
+// for every sector.  Lanes split the edges; the 16 minima are warp-reduced.
+//
+// The Q-network is 46x16 + 16x16 + 16x9 fp32: it runs on the FMA pipe.  Tensor
+// cores (tf32 / bf16 inputs) cannot hold the 1e-5 Q-value parity the path
+// requires, and at 1.2 kFLOP per env the layer is latency- not math-bound.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <string>
+
+#include "../../include/ttmpc.h"
+
+namespace ttdqn {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_SEG = 16;
+
+struct Args {
+  ttdqn_scene_layout lay;
+  int n_in, n_h1, n_h2, n_out;
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+  const double *agent, *poly_xy;
+  const int *poly_off, *is_solid, *n_poly;
+  const float *internal;
+  float *old_ext, *ext, *q;
+  int *action;
+  double *seg_dist, *ray_dist;
+  int n_envs;
+};
+
+__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) {
+  return ax * by - ay * bx;
+}
+
+struct Sector {  // per-sector constants in shared memory
+  double V[3][2];
+  double rx, ry;
+};
+
+__device__ __forceinline__ bool clip_to_triangle(const Sector &S, double p0x, double p0y, double dx,
+                                                 double dy, double &t0, double &t1) {
+  double lo = 0.0, hi = 1.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int j = (i + 1) % 3;
+    const double ex = S.V[j][0] - S.V[i][0], ey = S.V[j][1] - S.V[i][1];
+    const double f0 = cross2(ex, ey, p0x - S.V[i][0], p0y - S.V[i][1]);
+    const double f1 = cross2(ex, ey, dx, dy);
+    if (f1 == 0.0) {
+      if (f0 < 0.0) return false;
+    } else {
+      const double t = -f0 / f1;
+      if (f1 > 0.0) { if (t > lo) lo = t; }
+      else          { if (t < hi) hi = t; }
+    }
+    if (lo > hi) return false;
+  }
+  t0 = lo; t1 = hi;
+  return true;
+}
+
+__device__ __forceinline__ double ray_seg_hit(double ax, double ay, double rx, double ry, double L,
+                                              double p0x, double p0y, double p1x, double p1y) {
+  const double dx = p1x - p0x, dy = p1y - p0y;
+  const double wx = p0x - ax, wy = p0y - ay;
+  const double den = cross2(rx, ry, dx, dy);
+  if (den != 0.0) {
+    const double s = cross2(wx, wy, dx, dy) / den;
+    const double t = cross2(wx, wy, rx, ry) / den;
+    if (t >= 0.0 && t <= 1.0 && s >= 0.0 && s <= L) return s;
+    return INFINITY;
+  }
+  if (cross2(wx, wy, rx, ry) != 0.0) return INFINITY;
+  const double s0 = wx * rx + wy * ry, s1 = (p1x - ax) * rx + (p1y - ay) * ry;
+  const double lo = fmin(s0, s1), hi = fmax(s0, s1);
+  if (hi < 0.0 || lo > L) return INFINITY;
+  return fmax(lo, 0.0);
+}
+
+__device__ __forceinline__ float normalize_distance_f32(float d, float max_distance) {
+  float t = -2.0f * d;
+  t = t / max_distance;
+  t = expf(t);
+  t = 1.0f + t;
+  t = 2.0f / t;
+  return t - 1.0f;
+}
+
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// shared memory per block: Q-net weights (once) + per-warp scratch
+__global__ void __launch_bounds__(128) observe_act_kernel(const __grid_constant__ Args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ns = A.lay.num_segments;
+  const int n_ext = A.lay.use_memory ? 4 * ns : 2 * ns;
+  const int nw0 = A.n_in * A.n_h1, nw1 = A.n_h1 * A.n_h2, nw2 = A.n_h2 * A.n_out;
+  float *W0 = reinterpret_cast<float *>(smem_raw);
+  float *B0 = W0 + nw0, *W1 = B0 + A.n_h1, *B1 = W1 + nw1, *W2 = B1 + A.n_h2, *B2 = W2 + nw2;
+  size_t off = ((size_t)(nw0 + A.n_h1 + nw1 + A.n_h2 + nw2 + A.n_out) * sizeof(float) + 15) / 16 * 16;
+  const size_t per_warp = sizeof(Sector) * MAX_SEG + sizeof(float) * (size_t)(A.n_in + A.n_h1 + A.n_h2 + A.n_out + 4);
+  unsigned char *wbase = smem_raw + off + (size_t)warp * ((per_warp + 15) / 16 * 16);
+  Sector *sec = reinterpret_cast<Sector *>(wbase);
+  float *x = reinterpret_cast<float *>(wbase + sizeof(Sector) * MAX_SEG);
+  float *h1 = x + A.n_in, *h2 = h1 + A.n_h1, *qv = h2 + A.n_h2;
+
+  const bool have_net = A.w0 != nullptr;
+  if (have_net) {
+    for (int i = threadIdx.x; i < nw0; i += blockDim.x) W0[i] = A.w0[i];
+    for (int i = threadIdx.x; i < A.n_h1; i += blockDim.x) B0[i] = A.b0[i];
+    for (int i = threadIdx.x; i < nw1; i += blockDim.x) W1[i] = A.w1[i];
+    for (int i = threadIdx.x; i < A.n_h2; i += blockDim.x) B1[i] = A.b1[i];
+    for (int i = threadIdx.x; i < nw2; i += blockDim.x) W2[i] = A.w2[i];
+    for (int i = threadIdx.x; i < A.n_out; i += blockDim.x) B2[i] = A.b2[i];
+  }
+  __syncthreads();
+
+  const double L = A.lay.ray_length;
+  const double width = 2 * M_PI / ns;
+  for (int env = blockIdx.x * warps + warp; env < A.n_envs; env += gridDim.x * warps) {
+    const double ax = A.agent[3 * env], ay = A.agent[3 * env + 1], th = A.agent[3 * env + 2];
+    const double *xy = A.poly_xy + (size_t)env * A.lay.max_vert * 2;
+    const int *poff = A.poly_off + (size_t)env * (A.lay.max_poly + 1);
+    const int *solid = A.is_solid + (size_t)env * A.lay.max_poly;
+    const int npoly = A.n_poly[env];
+    if (lane < ns) {
+      const double angle = th + lane * width;
+      const double a1 = angle - width / 2, a2 = angle + width / 2;
+      Sector &S = sec[lane];
+      S.V[0][0] = ax; S.V[0][1] = ay;
+      S.V[1][0] = ax + L * cos(a1); S.V[1][1] = ay + L * sin(a1);
+      S.V[2][0] = ax + L * cos(a2); S.V[2][1] = ay + L * sin(a2);
+      S.rx = cos(angle); S.ry = sin(angle);
+    }
+    __syncwarp();
+    double dseg[MAX_SEG], dray[MAX_SEG];
+#pragma unroll
+    for (int i = 0; i < MAX_SEG; i++) { dseg[i] = INFINITY; dray[i] = INFINITY; }
+    bool inside_any = false;
+    for (int gidx = 0; gidx < npoly; gidx++) {
+      const int v0 = poff[gidx], nv = poff[gidx + 1] - v0;
+      if (nv < 2) continue;
+      const double *r = xy + 2 * (size_t)v0;
+      // even-odd point-in-ring, edges split over lanes
+      if (solid[gidx]) {
+        int cross = 0;
+        for (int e = lane; e < nv; e += 32) {
+          const int j = (e == 0) ? nv - 1 : e - 1;
+          const double xi = r[2 * e], yi = r[2 * e + 1], xj = r[2 * j], yj = r[2 * j + 1];
+          if (((yi > ay) != (yj > ay)) && (ax < (xj - xi) * (ay - yi) / (yj - yi) + xi)) cross ^= 1;
+        }
+        cross = __reduce_xor_sync(FULL, cross);
+        if (cross) { inside_any = true; continue; }
+      }
+      for (int e = lane; e < nv; e += 32) {
+        const int e2 = (e + 1 == nv) ? 0 : e + 1;
+        const double p0x = r[2 * e], p0y = r[2 * e + 1], p1x = r[2 * e2], p1y = r[2 * e2 + 1];
+        const double dx = p1x - p0x, dy = p1y - p0y;
+        const double dd = dx * dx + dy * dy;
+#pragma unroll
+        for (int i = 0; i < MAX_SEG; i++) {
+          if (i < ns) {
+            const Sector &S = sec[i];
+            double t0, t1;
+            if (clip_to_triangle(S, p0x, p0y, dx, dy, t0, t1)) {
+              double t = t0;
+              if (dd > 0.0) {
+                t = ((ax - p0x) * dx + (ay - p0y) * dy) / dd;
+                t = fmin(fmax(t, t0), t1);
+              }
+              const double qx = p0x + t * dx - ax, qy = p0y + t * dy - ay;
+              dseg[i] = fmin(dseg[i], sqrt(qx * qx + qy * qy));
+            }
+            dray[i] = fmin(dray[i], ray_seg_hit(ax, ay, S.rx, S.ry, L, p0x, p0y, p1x, p1y));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_SEG; i++) {
+      if (i < ns) {
+        double s = wmin(dseg[i]), r_ = wmin(dray[i]);
+        if (inside_any) { s = 0.0; r_ = 0.0; }
+        if (lane == 0) {
+          if (A.seg_dist) A.seg_dist[(size_t)env * ns + i] = s;
+          if (A.ray_dist) A.ray_dist[(size_t)env * ns + i] = r_;
+          x[i] = normalize_distance_f32((float)s, (float)A.lay.max_distance);
+          x[ns + i] = normalize_distance_f32((float)r_, (float)A.lay.max_distance);
+        }
+      }
+    }
+    __syncwarp();
+    if (A.lay.use_memory) {
+      float *old = A.old_ext + (size_t)env * 2 * ns;
+      for (int i = lane; i < 2 * ns; i += 32) {
+        x[2 * ns + i] = old[i];
+        old[i] = x[i];
+      }
+    }
+    for (int i = lane; i < A.lay.n_internal; i += 32)
+      x[n_ext + i] = A.internal ? A.internal[(size_t)env * A.lay.n_internal + i] : 0.0f;
+    __syncwarp();
+    if (A.ext)
+      for (int i = lane; i < n_ext; i += 32) A.ext[(size_t)env * n_ext + i] = x[i];
+    if (have_net) {
+      for (int o = lane; o < A.n_h1; o += 32) {
+        float acc = B0[o];
+        for (int i = 0; i < A.n_in; i++) acc += W0[o * A.n_in + i] * x[i];
+        h1[o] = acc < 0.0f ? 0.0f : acc;
+      }
+      __syncwarp();
+      for (int o = lane; o < A.n_h2; o += 32) {
+        float acc = B1[o];
+        for (int i = 0; i < A.n_h1; i++) acc += W1[o * A.n_h1 + i] * h1[i];
+        h2[o] = acc < 0.0f ? 0.0f : acc;
+      }
+      __syncwarp();
+      for (int o = lane; o < A.n_out; o += 32) {
+        float acc = B2[o];
+        for (int i = 0; i < A.n_h2; i++) acc += W2[o * A.n_h2 + i] * h2[i];
+        qv[o] = acc;
+        if (A.q) A.q[(size_t)env * A.n_out + o] = acc;
+      }
+      __syncwarp();
+      if (lane == 0 && A.action) {
+        int best = 0;
+        for (int o = 1; o < A.n_out; o++)
+          if (qv[o] > qv[best]) best = o;
+        A.action[env] = best;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace ttdqn
+
+static thread_local std::string g_dqn_err;
+extern "C" const char *ttdqn_last_error(void) { return g_dqn_err.c_str(); }
+static int dfail(int code, const std::string &m) { g_dqn_err = m; return code; }
+#define DQN_TRY(x)                                                                   \
+  do {                                                                               \
+    cudaError_t e__ = (x);                                                           \
+    if (e__ != cudaSuccess)                                                          \
+      return dfail(TTMPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" void ttdqn_default_layout(ttdqn_scene_layout *l) {
+  l->num_segments = 8; l->max_poly = 16; l->max_vert = 512; l->n_internal = 14;
+  l->use_memory = 1; l->_pad = 0; l->ray_length = 1000.0; l->max_distance = 10.0;
+}
+
+extern "C" int ttdqn_observe_act_device(const ttdqn_scene_layout *lay, const ttdqn_qnet *qn, int n,
+                                        const double *d_agent, const double *d_poly_xy,
+                                        const int *d_poly_off, const int *d_is_solid,
+                                        const int *d_n_poly, const float *d_internal,
+                                        float *d_old_ext, float *d_ext, float *d_q, int *d_action,
+                                        double *d_seg, double *d_ray, void *stream) {
+  using namespace ttdqn;
+  if (!lay || n < 0) return dfail(TTMPC_ERR_BAD_ARG, "layout required, n >= 0");
+  if (lay->num_segments < 1 || lay->num_segments > MAX_SEG)
+    return dfail(TTMPC_ERR_BAD_CONFIG, "num_segments must be in 1..16");
+  if (lay->use_memory && !d_old_ext) return dfail(TTMPC_ERR_BAD_ARG, "use_memory needs d_old_ext");
+  if (n == 0) return TTMPC_OK;
+  if (!d_agent || !d_poly_xy || !d_poly_off || !d_is_solid || !d_n_poly)
+    return dfail(TTMPC_ERR_BAD_ARG, "agent and geometry pointers are required");
+  Args A;
+  A.lay = *lay;
+  const int n_ext = lay->use_memory ? 4 * lay->num_segments : 2 * lay->num_segments;
+  if (qn) {
+    if (qn->n_in != n_ext + lay->n_internal)
+      return dfail(TTMPC_ERR_BAD_CONFIG, "qnet n_in must equal n_ext + n_internal");
+    if (qn->n_h1 < 1 || qn->n_h2 < 1 || qn->n_out < 1 || qn->n_h1 > 256 || qn->n_h2 > 256 || qn->n_out > 64)
+      return dfail(TTMPC_ERR_BAD_CONFIG, "qnet layer sizes out of range");
+    A.n_in = qn->n_in; A.n_h1 = qn->n_h1; A.n_h2 = qn->n_h2; A.n_out = qn->n_out;
+    A.w0 = qn->w0; A.b0 = qn->b0; A.w1 = qn->w1; A.b1 = qn->b1; A.w2 = qn->w2; A.b2 = qn->b2;
+  } else {
+    A.n_in = n_ext + lay->n_internal; A.n_h1 = 1; A.n_h2 = 1; A.n_out = 1;
+    A.w0 = A.b0 = A.w1 = A.b1 = A.w2 = A.b2 = nullptr;
+  }
+  A.agent = d_agent; A.poly_xy = d_poly_xy; A.poly_off = d_poly_off; A.is_solid = d_is_solid;
+  A.n_poly = d_n_poly; A.internal = d_internal; A.old_ext = d_old_ext; A.ext = d_ext; A.q = d_q;
+  A.action = d_action; A.seg_dist = d_seg; A.ray_dist = d_ray; A.n_envs = n;
+  const int warps = 4;
+  size_t wbytes = ((size_t)(A.n_in * A.n_h1 + A.n_h1 + A.n_h1 * A.n_h2 + A.n_h2 + A.n_h2 * A.n_out + A.n_out) * sizeof(float) + 15) / 16 * 16;
+  size_t per_warp = (sizeof(Sector) * MAX_SEG + sizeof(float) * (size_t)(A.n_in + A.n_h1 + A.n_h2 + A.n_out + 4) + 15) / 16 * 16;
+  size_t smem = wbytes + per_warp * warps;
+  int dev = 0, sms = 0;
+  DQN_TRY(cudaGetDevice(&dev));
+  DQN_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DQN_TRY(cudaFuncSetAttribute(observe_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  DQN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, observe_act_kernel, warps * 32, smem));
+  if (bps < 1) return dfail(TTMPC_ERR_UNSUPPORTED, "observe_act kernel does not fit");
+  long long want = ((long long)n + warps - 1) / warps, cap = (long long)sms * bps;
+  const int grid = (int)(want < cap ? want : cap);
+  observe_act_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(A);
+  DQN_TRY(cudaGetLastError());
+  return TTMPC_OK;
+}
+
+extern "C" int ttdqn_observe_act_host(const ttdqn_scene_layout *lay, const ttdqn_qnet *qn, int n,
+                                      const double *h_agent, const double *h_poly_xy,
+                                      const int *h_poly_off, const int *h_is_solid,
+                                      const int *h_n_poly, const float *h_internal,
+                                      float *h_old_ext, float *h_ext, float *h_q, int *h_action,
+                                      double *h_seg, double *h_ray) {
+  if (!lay || n < 0) return dfail(TTMPC_ERR_BAD_ARG, "layout required, n >= 0");
+  if (n == 0) return TTMPC_OK;
+  const size_t nn = (size_t)n;
+  const int ns = lay->num_segments;
+  const int n_ext = lay->use_memory ? 4 * ns : 2 * ns;
+  std::string err;
+  void *ptrs[32]; int np = 0;
+  auto dalloc = [&](size_t bytes, const void *src) -> void * {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes ? bytes : 8) != cudaSuccess) { err = "cudaMalloc failed"; return nullptr; }
+    ptrs[np++] = d;
+    if (src && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) err = "H2D copy failed";
+    return d;
+  };
+  auto cleanup = [&]() { for (int i = 0; i < np; i++) cudaFree(ptrs[i]); };
+  double *dag = (double *)dalloc(sizeof(double) * 3 * nn, h_agent);
+  double *dxy = (double *)dalloc(sizeof(double) * 2 * nn * lay->max_vert, h_poly_xy);
+  int *doff = (int *)dalloc(sizeof(int) * nn * (lay->max_poly + 1), h_poly_off);
+  int *dsol = (int *)dalloc(sizeof(int) * nn * lay->max_poly, h_is_solid);
+  int *dnp = (int *)dalloc(sizeof(int) * nn, h_n_poly);
+  float *dint = h_internal ? (float *)dalloc(sizeof(float) * nn * lay->n_internal, h_internal) : nullptr;
+  float *dold = lay->use_memory ? (float *)dalloc(sizeof(float) * nn * 2 * ns, h_old_ext) : nullptr;
+  float *dext = (float *)dalloc(sizeof(float) * nn * n_ext, nullptr);
+  double *dseg = (double *)dalloc(sizeof(double) * nn * ns, nullptr);
+  double *dray = (double *)dalloc(sizeof(double) * nn * ns, nullptr);
+  ttdqn_qnet dq; float *dqv = nullptr; int *dact = nullptr;
+  if (qn) {
+    dq = *qn;
+    dq.w0 = (float *)dalloc(sizeof(float) * qn->n_in * qn->n_h1, qn->w0);
+    dq.b0 = (float *)dalloc(sizeof(float) * qn->n_h1, qn->b0);
+    dq.w1 = (float *)dalloc(sizeof(float) * qn->n_h1 * qn->n_h2, qn->w1);
+    dq.b1 = (float *)dalloc(sizeof(float) * qn->n_h2, qn->b1);
+    dq.w2 = (float *)dalloc(sizeof(float) * qn->n_h2 * qn->n_out, qn->w2);
+    dq.b2 = (float *)dalloc(sizeof(float) * qn->n_out, qn->b2);
+    dqv = (float *)dalloc(sizeof(float) * nn * qn->n_out, nullptr);
+    dact = (int *)dalloc(sizeof(int) * nn, nullptr);
+  }
+  if (!err.empty()) { cleanup(); return dfail(TTMPC_ERR_CUDA, err); }
+  int rc = ttdqn_observe_act_device(lay, qn ? &dq : nullptr, n, dag, dxy, doff, dsol, dnp, dint, dold,
+                                    dext, dqv, dact, dseg, dray, 0);
+  if (rc) { cleanup(); return rc; }
+  cudaError_t e = cudaDeviceSynchronize();
+  auto back = [&](void *h, const void *d, size_t bytes) {
+    if (h && d && e == cudaSuccess) e = cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost);
+  };
+  back(h_ext, dext, sizeof(float) * nn * n_ext);
+  back(h_seg, dseg, sizeof(double) * nn * ns);
+  back(h_ray, dray, sizeof(double) * nn * ns);
+  if (lay->use_memory) back(h_old_ext, dold, sizeof(float) * nn * 2 * ns);
+  if (qn) { back(h_q, dqv, sizeof(float) * nn * qn->n_out); back(h_action, dact, sizeof(int) * nn); }
+  cleanup();
+  if (e != cudaSuccess) return dfail(TTMPC_ERR_CUDA, cudaGetErrorString(e));
+  return TTMPC_OK;
+}

@@ -1,0 +1,417 @@
+// ttmpc_api.cu -- the C-ABI (include/ttmpc.h) over the sm_100a kernels.
+// Host-side only: argument checking, workspace management, staging copies.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ttmpc_device.cuh"
+#include "ttmpc_launch.cuh"
+
+using namespace ttmpc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                     \
+  do {                                                                                  \
+    cudaError_t e__ = (x);                                                              \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(TTMPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+
+extern "C" const char *ttmpc_last_error(void) { return g_err.c_str(); }
+extern "C" int ttmpc_version(void) { return TTMPC_VERSION; }
+extern "C" const char *ttmpc_exit_status_name(int code) {
+  switch (code) {
+    case TTMPC_CONVERGED: return "Converged";
+    case TTMPC_NOT_CONVERGED_ITERATIONS: return "NotConvergedIterations";
+    case TTMPC_NOT_CONVERGED_OUT_OF_TIME: return "NotConvergedOutOfTime";
+    case TTMPC_NOT_FINITE: return "NotFiniteComputation";
+    default: return "Unknown";
+  }
+}
+
+// config/mpc_default.yaml + opengen 0.7.1 SolverConfiguration defaults, with
+// initial_penalty 10 as set at mpc_generator.py:269.
+extern "C" void ttmpc_default_config(ttmpc_config *c) {
+  std::memset(c, 0, sizeof(*c));
+  c->N_hor = 20; c->nu = 2; c->ns = 3; c->nq = 10;
+  c->Nother = 10; c->Nstcobs = 10; c->nstcobs = 12; c->Ndynobs = 15; c->ndynobs = 6;
+  c->ts = 0.2; c->vehicle_width = 0.5; c->social_margin = 0.2;
+  c->lin_vel_min = -0.5; c->lin_vel_max = 1.5; c->ang_vel_max = 0.5;
+  c->lin_acc_min = -1.0; c->lin_acc_max = 1.0; c->ang_acc_max = 3.0;
+  c->tolerance = 1e-4; c->initial_tolerance = 1e-4; c->delta_tolerance = 1e-4;
+  c->initial_penalty = 10.0; c->penalty_update_factor = 5.0;
+  c->inner_tolerance_update_factor = 0.1; c->sufficient_decrease_coeff = 0.1;
+  c->lbfgs_memory = 10; c->max_inner_iterations = 500; c->max_outer_iterations = 10;
+}
+extern "C" int ttmpc_num_params(const ttmpc_config *c) {
+  const int N = c->N_hor;
+  return 2 * c->ns + c->nu + c->nq + c->ns * N + N + c->ns * N * c->Nother +
+         c->Nstcobs * c->nstcobs + c->Ndynobs * c->ndynobs * N + 2 * N;
+}
+extern "C" int ttmpc_num_decision(const ttmpc_config *c) { return c->nu * c->N_hor; }
+extern "C" int ttmpc_num_alm(const ttmpc_config *c) { return 2 * c->N_hor; }
+extern "C" int ttmpc_num_penalty(const ttmpc_config *c) { return c->Ndynobs; }
+
+static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
+  if (!c) return fail(TTMPC_ERR_BAD_CONFIG, "null config");
+  if (c->nu != 2 || c->ns != 3 || c->nq != 10 || c->ndynobs != 6)
+    return fail(TTMPC_ERR_BAD_CONFIG, "nu/ns/nq/ndynobs must be 2/3/10/6 (unicycle, mpc_generator.py layout)");
+  if (c->N_hor < 1 || c->N_hor > 32) return fail(TTMPC_ERR_BAD_CONFIG, "N_hor must be in 1..32");
+  if (c->nstcobs % 3 != 0 || c->nstcobs / 3 > MAX_EDGE || (c->Nstcobs > 0 && c->nstcobs < 3))
+    return fail(TTMPC_ERR_BAD_CONFIG, "nstcobs must be 3*edges with edges <= 8");
+  if (c->Nother < 0 || c->Nstcobs < 0 || c->Ndynobs < 0 || c->Ndynobs > 64)
+    return fail(TTMPC_ERR_BAD_CONFIG, "obstacle counts out of range (Ndynobs <= 64)");
+  if (c->lbfgs_memory < 1 || c->lbfgs_memory > MAX_MEM)
+    return fail(TTMPC_ERR_BAD_CONFIG, "lbfgs_memory must be in 1..16");
+  if (c->max_inner_iterations < 1 || c->max_outer_iterations < 1 || !(c->ts > 0.0))
+    return fail(TTMPC_ERR_BAD_CONFIG, "iteration limits and ts must be positive");
+  const int N = c->N_hor;
+  g->N = N; g->Nother = c->Nother; g->Nstc = c->Nstcobs; g->nstcobs = c->nstcobs;
+  g->ne = c->nstcobs / 3; g->Ndyn = c->Ndynobs; g->mem = c->lbfgs_memory;
+  g->max_inner = c->max_inner_iterations; g->max_outer = c->max_outer_iterations;
+  g->off_s = 0; g->off_q = 2 * c->ns + c->nu; g->off_r = g->off_q + c->nq;
+  g->off_vref = g->off_r + c->ns * N; g->off_c = g->off_vref + N;
+  g->off_os = g->off_c + c->ns * N * c->Nother;
+  g->off_od = g->off_os + c->Nstcobs * c->nstcobs;
+  g->off_qdyn = g->off_od + c->Ndynobs * c->ndynobs * N + N;
+  g->np = g->off_qdyn + N;
+  g->warps_per_block = 4;
+  g->smem_per_warp = smem_bytes_per_warp(N, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
+  g->ts = c->ts; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;
+  g->vmin = c->lin_vel_min; g->vmax = c->lin_vel_max; g->wmax = c->ang_vel_max;
+  g->amin = c->lin_acc_min; g->amax = c->lin_acc_max; g->awmax = c->ang_acc_max;
+  g->tol = c->tolerance; g->init_tol = c->initial_tolerance; g->delta_tol = c->delta_tolerance;
+  g->c0 = c->initial_penalty; g->pen_factor = c->penalty_update_factor;
+  g->tol_factor = c->inner_tolerance_update_factor; g->suff_dec = c->sufficient_decrease_coeff;
+  return TTMPC_OK;
+}
+
+// ---------------------------------------------------------------- per-device workspace
+struct Workspace {
+  int device = -1;
+  int sm_count = 0;
+  double *dyn_scratch = nullptr; size_t dyn_bytes = 0;
+  int *work_counter = nullptr;
+  unsigned long long *stats = nullptr;
+  // device staging for the host API
+  void *dbuf = nullptr; size_t dbytes = 0;
+  void *hbuf = nullptr; size_t hbytes = 0;
+};
+static std::mutex g_mu;
+static std::vector<Workspace> g_ws;
+
+static int get_ws(Workspace **out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  for (auto &w : g_ws)
+    if (w.device == dev) { *out = &w; return TTMPC_OK; }
+  Workspace w;
+  w.device = dev;
+  CUDA_TRY(cudaDeviceGetAttribute(&w.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaMalloc(&w.work_counter, 64));
+  CUDA_TRY(cudaMalloc(&w.stats, 64));
+  CUDA_TRY(cudaMemset(w.stats, 0, 64));
+  g_ws.reserve(16);
+  g_ws.push_back(w);
+  *out = &g_ws.back();
+  return TTMPC_OK;
+}
+static int ensure_dyn(Workspace *w, size_t bytes) {
+  if (bytes <= w->dyn_bytes) return TTMPC_OK;
+  if (w->dyn_scratch) CUDA_TRY(cudaFree(w->dyn_scratch));
+  w->dyn_scratch = nullptr; w->dyn_bytes = 0;
+  CUDA_TRY(cudaMalloc(&w->dyn_scratch, bytes));
+  w->dyn_bytes = bytes;
+  return TTMPC_OK;
+}
+static int ensure_staging(Workspace *w, size_t bytes) {
+  if (bytes > w->dbytes) {
+    if (w->dbuf) CUDA_TRY(cudaFree(w->dbuf));
+    w->dbuf = nullptr; w->dbytes = 0;
+    CUDA_TRY(cudaMalloc(&w->dbuf, bytes));
+    w->dbytes = bytes;
+  }
+  if (bytes > w->hbytes) {
+    if (w->hbuf) CUDA_TRY(cudaFreeHost(w->hbuf));
+    w->hbuf = nullptr; w->hbytes = 0;
+    CUDA_TRY(cudaHostAlloc(&w->hbuf, bytes, cudaHostAllocDefault));
+    w->hbytes = bytes;
+  }
+  return TTMPC_OK;
+}
+
+static int grid_for(Workspace *w, const DevCfg &g, int n_scenes, int *grid) {
+  int bps = 0;
+  CUDA_TRY(solve_occupancy(g, &bps));
+  if (bps < 1) return fail(TTMPC_ERR_UNSUPPORTED, "configuration does not fit in shared memory");
+  long long want = ((long long)n_scenes + g.warps_per_block - 1) / g.warps_per_block;
+  long long cap = (long long)w->sm_count * bps;
+  *grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  return TTMPC_OK;
+}
+
+extern "C" int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes, const double *d_p,
+                                        int use_u0, int use_y0, const double *d_c0,
+                                        const ttmpc_result *res, void *stream) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  if (n_scenes < 0 || !res || !res->u || (n_scenes > 0 && !d_p))
+    return fail(TTMPC_ERR_BAD_ARG, "n_scenes >= 0, d_p and res->u are required");
+  if (n_scenes == 0) return TTMPC_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace *w;
+  rc = get_ws(&w);
+  if (rc) return rc;
+  int grid;
+  rc = grid_for(w, g, n_scenes, &grid);
+  if (rc) return rc;
+  const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
+  rc = ensure_dyn(w, (table ? table : 8) * (size_t)grid * g.warps_per_block);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
+  SolveArgs A;
+  A.p = d_p; A.c0 = d_c0; A.u = res->u; A.y = res->y; A.cost = res->cost;
+  A.last_fpr = res->last_fpr; A.f1_infeas = res->f1_infeas; A.f2_norm = res->f2_norm;
+  A.penalty = res->penalty; A.exit_status = res->exit_status; A.outer_iters = res->outer_iters;
+  A.inner_iters = res->inner_iters; A.pred_states = res->pred_states; A.evals = res->evals;
+  A.dyn_scratch = w->dyn_scratch; A.work_counter = w->work_counter; A.stats = w->stats;
+  A.n_scenes = n_scenes; A.use_u0 = use_u0; A.use_y0 = use_y0;
+  CUDA_TRY(launch_solve(g, A, grid, st));
+  return TTMPC_OK;
+}
+
+// Cumulative device-side counters since the last reset:
+// [0] cost-only evaluations [1] cost+gradient evaluations [2] dynamic-obstacle
+// bodies executed [3] PANOC iterations.  Synchronises the device.
+extern "C" int ttmpc_read_stats(unsigned long long out[4], int reset) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace *w;
+  int rc = get_ws(&w);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, w->stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 64));
+  return TTMPC_OK;
+}
+
+// Launch geometry the solve kernel would use (for DESIGN/bench reporting).
+extern "C" int ttmpc_launch_info(const ttmpc_config *cfg, int n_scenes, int *grid, int *block,
+                                 int *smem_bytes, int *blocks_per_sm, int *sm_count) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace *w;
+  rc = get_ws(&w);
+  if (rc) return rc;
+  int gr;
+  rc = grid_for(w, g, n_scenes, &gr);
+  if (rc) return rc;
+  int bps = 0;
+  CUDA_TRY(solve_occupancy(g, &bps));
+  if (grid) *grid = gr;
+  if (block) *block = g.warps_per_block * 32;
+  if (smem_bytes) *smem_bytes = g.smem_per_warp * g.warps_per_block;
+  if (blocks_per_sm) *blocks_per_sm = bps;
+  if (sm_count) *sm_count = w->sm_count;
+  return TTMPC_OK;
+}
+
+namespace {
+struct Carver {
+  char *d, *h; size_t off = 0;
+  template <class T> void take(size_t n, T **dp, T **hp) {
+    off = (off + 255) / 256 * 256;
+    *dp = reinterpret_cast<T *>(d + off);
+    *hp = reinterpret_cast<T *>(h + off);
+    off += n * sizeof(T);
+  }
+};
+}  // namespace
+
+extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const double *h_p,
+                                      int use_u0, int use_y0, const double *h_c0,
+                                      const ttmpc_result *res) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  if (n < 0 || !res || !res->u || (n > 0 && !h_p))
+    return fail(TTMPC_ERR_BAD_ARG, "n >= 0, h_p and res->u are required");
+  if (n == 0) return TTMPC_OK;
+  const size_t nn = (size_t)n, nu = 2 * (size_t)g.N;
+  size_t total = 4096 + 256 * 16 + sizeof(double) * (nn * g.np + nn + 2 * nn * nu + 5 * nn + nn * g.N * 3) +
+                 sizeof(int) * 3 * nn + sizeof(long long) * 2 * nn;
+  Workspace *w;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    rc = get_ws(&w);
+    if (rc) return rc;
+    rc = ensure_staging(w, total);
+    if (rc) return rc;
+  }
+  Carver cv{(char *)w->dbuf, (char *)w->hbuf};
+  double *dp, *hp, *dc0, *hc0, *du, *hu, *dy, *hy, *dcost, *hcost, *dfpr, *hfpr, *df1, *hf1, *df2,
+      *hf2, *dpen, *hpen, *dps, *hps;
+  int *dex, *hex, *dout, *hout, *din, *hin;
+  long long *dev, *hev;
+  cv.take(nn * g.np, &dp, &hp);
+  cv.take(nn, &dc0, &hc0);
+  cv.take(nn * nu, &du, &hu);
+  cv.take(nn * nu, &dy, &hy);
+  cv.take(nn, &dcost, &hcost);
+  cv.take(nn, &dfpr, &hfpr);
+  cv.take(nn, &df1, &hf1);
+  cv.take(nn, &df2, &hf2);
+  cv.take(nn, &dpen, &hpen);
+  cv.take(nn * g.N * 3, &dps, &hps);
+  cv.take(nn, &dex, &hex);
+  cv.take(nn, &dout, &hout);
+  cv.take(nn, &din, &hin);
+  cv.take(2 * nn, &dev, &hev);
+  cudaStream_t st = 0;
+  std::memcpy(hp, h_p, sizeof(double) * nn * g.np);
+  CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * nn * g.np, cudaMemcpyHostToDevice, st));
+  if (h_c0) {
+    std::memcpy(hc0, h_c0, sizeof(double) * nn);
+    CUDA_TRY(cudaMemcpyAsync(dc0, hc0, sizeof(double) * nn, cudaMemcpyHostToDevice, st));
+  }
+  if (use_u0) {
+    std::memcpy(hu, res->u, sizeof(double) * nn * nu);
+    CUDA_TRY(cudaMemcpyAsync(du, hu, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
+  }
+  if (use_y0 && res->y) {
+    std::memcpy(hy, res->y, sizeof(double) * nn * nu);
+    CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
+  }
+  ttmpc_result dres;
+  std::memset(&dres, 0, sizeof(dres));
+  dres.u = du; dres.y = res->y ? dy : nullptr; dres.cost = dcost; dres.exit_status = dex;
+  dres.outer_iters = dout; dres.inner_iters = din; dres.last_fpr = dfpr; dres.f1_infeas = df1;
+  dres.f2_norm = df2; dres.penalty = dpen; dres.pred_states = res->pred_states ? dps : nullptr;
+  dres.evals = dev;
+  rc = ttmpc_solve_batch_device(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st);
+  if (rc) return rc;
+  // one contiguous D2H of everything after the inputs
+  const size_t out_begin = (size_t)((char *)du - (char *)w->dbuf);
+  CUDA_TRY(cudaMemcpyAsync((char *)w->hbuf + out_begin, (char *)w->dbuf + out_begin, cv.off - out_begin,
+                           cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  std::memcpy(res->u, hu, sizeof(double) * nn * nu);
+  if (res->y) std::memcpy(res->y, hy, sizeof(double) * nn * nu);
+  if (res->cost) std::memcpy(res->cost, hcost, sizeof(double) * nn);
+  if (res->last_fpr) std::memcpy(res->last_fpr, hfpr, sizeof(double) * nn);
+  if (res->f1_infeas) std::memcpy(res->f1_infeas, hf1, sizeof(double) * nn);
+  if (res->f2_norm) std::memcpy(res->f2_norm, hf2, sizeof(double) * nn);
+  if (res->penalty) std::memcpy(res->penalty, hpen, sizeof(double) * nn);
+  if (res->pred_states) std::memcpy(res->pred_states, hps, sizeof(double) * nn * g.N * 3);
+  if (res->exit_status) std::memcpy(res->exit_status, hex, sizeof(int) * nn);
+  if (res->outer_iters) std::memcpy(res->outer_iters, hout, sizeof(int) * nn);
+  if (res->inner_iters) std::memcpy(res->inner_iters, hin, sizeof(int) * nn);
+  if (res->evals) std::memcpy(res->evals, hev, sizeof(long long) * 2 * nn);
+  return TTMPC_OK;
+}
+
+extern "C" int ttmpc_eval_batch_device(const ttmpc_config *cfg, int n, const double *d_p,
+                                       const double *d_u, const double *d_c, const double *d_y,
+                                       double *d_f, double *d_F1, double *d_F2, double *d_psi,
+                                       double *d_grad, void *stream) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!d_p || !d_u))) return fail(TTMPC_ERR_BAD_ARG, "d_p and d_u are required");
+  if (n == 0) return TTMPC_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace *w;
+  rc = get_ws(&w);
+  if (rc) return rc;
+  int grid;
+  rc = grid_for(w, g, n, &grid);
+  if (rc) return rc;
+  const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
+  rc = ensure_dyn(w, (table ? table : 8) * (size_t)grid * g.warps_per_block);
+  if (rc) return rc;
+  EvalArgs A;
+  A.p = d_p; A.u = d_u; A.c = d_c; A.y = d_y; A.f = d_f; A.F1 = d_F1; A.F2 = d_F2; A.psi = d_psi;
+  A.grad = d_grad; A.dyn_scratch = w->dyn_scratch; A.n_scenes = n;
+  CUDA_TRY(launch_eval(g, A, grid, (cudaStream_t)stream));
+  return TTMPC_OK;
+}
+
+extern "C" int ttmpc_eval_batch_host(const ttmpc_config *cfg, int n, const double *h_p,
+                                     const double *h_u, const double *h_c, const double *h_y,
+                                     double *h_f, double *h_F1, double *h_F2, double *h_psi,
+                                     double *h_grad) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!h_p || !h_u))) return fail(TTMPC_ERR_BAD_ARG, "h_p and h_u are required");
+  if (n == 0) return TTMPC_OK;
+  const size_t nn = (size_t)n, nu = 2 * (size_t)g.N;
+  double *dp = nullptr, *du = nullptr, *dc = nullptr, *dy = nullptr, *df = nullptr, *dF1 = nullptr,
+         *dF2 = nullptr, *dpsi = nullptr, *dgrad = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dp); cudaFree(du); cudaFree(dc); cudaFree(dy); cudaFree(df); cudaFree(dF1);
+    cudaFree(dF2); cudaFree(dpsi); cudaFree(dgrad);
+  };
+#define TRY_OR_CLEAN(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { cleanup(); return fail(TTMPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e__)); } } while (0)
+  TRY_OR_CLEAN(cudaMalloc(&dp, sizeof(double) * nn * g.np));
+  TRY_OR_CLEAN(cudaMalloc(&du, sizeof(double) * nn * nu));
+  TRY_OR_CLEAN(cudaMalloc(&dc, sizeof(double) * nn));
+  TRY_OR_CLEAN(cudaMalloc(&dy, sizeof(double) * nn * nu));
+  TRY_OR_CLEAN(cudaMalloc(&df, sizeof(double) * nn));
+  TRY_OR_CLEAN(cudaMalloc(&dF1, sizeof(double) * nn * nu));
+  TRY_OR_CLEAN(cudaMalloc(&dF2, sizeof(double) * nn * (g.Ndyn > 0 ? g.Ndyn : 1)));
+  TRY_OR_CLEAN(cudaMalloc(&dpsi, sizeof(double) * nn));
+  TRY_OR_CLEAN(cudaMalloc(&dgrad, sizeof(double) * nn * nu));
+  TRY_OR_CLEAN(cudaMemcpy(dp, h_p, sizeof(double) * nn * g.np, cudaMemcpyHostToDevice));
+  TRY_OR_CLEAN(cudaMemcpy(du, h_u, sizeof(double) * nn * nu, cudaMemcpyHostToDevice));
+  if (h_c) TRY_OR_CLEAN(cudaMemcpy(dc, h_c, sizeof(double) * nn, cudaMemcpyHostToDevice));
+  if (h_y) TRY_OR_CLEAN(cudaMemcpy(dy, h_y, sizeof(double) * nn * nu, cudaMemcpyHostToDevice));
+  rc = ttmpc_eval_batch_device(cfg, n, dp, du, h_c ? dc : nullptr, h_y ? dy : nullptr, df, dF1, dF2,
+                               dpsi, dgrad, 0);
+  if (rc) { cleanup(); return rc; }
+  TRY_OR_CLEAN(cudaDeviceSynchronize());
+  if (h_f) TRY_OR_CLEAN(cudaMemcpy(h_f, df, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+  if (h_F1) TRY_OR_CLEAN(cudaMemcpy(h_F1, dF1, sizeof(double) * nn * nu, cudaMemcpyDeviceToHost));
+  if (h_F2 && g.Ndyn) TRY_OR_CLEAN(cudaMemcpy(h_F2, dF2, sizeof(double) * nn * g.Ndyn, cudaMemcpyDeviceToHost));
+  if (h_psi) TRY_OR_CLEAN(cudaMemcpy(h_psi, dpsi, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+  if (h_grad) TRY_OR_CLEAN(cudaMemcpy(h_grad, dgrad, sizeof(double) * nn * nu, cudaMemcpyDeviceToHost));
+  cleanup();
+  return TTMPC_OK;
+}
+
+extern "C" int ttmpc_measure_fp64_peak(double *tflops, void *stream) {
+  if (!tflops) return fail(TTMPC_ERR_BAD_ARG, "null output");
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int threads = 256, blocks = sms * 8, iters = 1 << 15;
+  double *out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, sizeof(double) * threads * blocks));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    CUDA_TRY(launch_fp64_peak(out, blocks, threads, iters, st));
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+    double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return TTMPC_OK;
+}

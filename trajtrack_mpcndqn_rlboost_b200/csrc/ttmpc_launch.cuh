@@ -1,0 +1,36 @@
+// ttmpc_launch.cuh -- kernel argument blocks and host launch helpers shared by
+// ttmpc_solve.cu (kernels) and ttmpc_api.cu (C-ABI).
+#pragma once
+#include "ttmpc_device.cuh"
+
+namespace ttmpc {
+
+struct SolveArgs {
+  const double *p;      // [n][np]
+  const double *c0;     // [n] or null
+  double *u;            // [n][2N] in/out
+  double *y;            // [n][2N] in/out or null
+  double *cost, *last_fpr, *f1_infeas, *f2_norm, *penalty;
+  int *exit_status, *outer_iters, *inner_iters;
+  double *pred_states;  // [n][N][3] or null
+  long long *evals;     // [n][2] or null
+  double *dyn_scratch;  // [total_warps][DYN_FIELDS*Ndyn*N]
+  int *work_counter;    // dynamic scene queue
+  unsigned long long *stats;  // [4]: cost evals, grad evals, dyn bodies, panoc iterations
+  int n_scenes;
+  int use_u0, use_y0;
+};
+
+struct EvalArgs {
+  const double *p, *u, *c, *y;
+  double *f, *F1, *F2, *psi, *grad;
+  double *dyn_scratch;
+  int n_scenes;
+};
+
+cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st);
+cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream_t st);
+cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm);
+cudaError_t launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t st);
+
+}  // namespace ttmpc

@@ -1,0 +1,488 @@
+// ttmpc_solve.cu -- persistent warp-per-scene PANOC + ALM/PM solve kernel and the
+// batched evaluation kernel.  See ttmpc_device.cuh for the data layout.
+//
+// Solver structure follows OpEn (optimization_engine 0.7.x), the solver the
+// reference calls at src/mpc_traj_tracker/trajectory_generator.py:284:
+//   outer loop  : AlmOptimizer::solve / step       (alm_optimizer.rs)
+//   inner loop  : PANOCOptimizer::solve, PANOCEngine::{init,step} (panoc_*.rs)
+//   direction   : lbfgs crate two-loop recursion with C-BFGS safeguard
+// but is laid out for a warp: vectors are 2 registers per lane, the L-BFGS
+// history is a ring of double2 rows in shared memory, dot products are
+// butterfly all-reduces.
+#include "ttmpc_device.cuh"
+#include "ttmpc_launch.cuh"
+
+namespace ttmpc {
+
+// PANOC constants (panoc_engine.rs)
+constexpr double GAMMA_L_COEFF = 0.95;
+constexpr double DELTA_LIPSCHITZ = 1e-12;
+constexpr double EPSILON_LIPSCHITZ = 1e-6;
+constexpr double LIPSCHITZ_UPDATE_EPSILON = 1e-6;
+constexpr int MAX_LIPSCHITZ_UPDATE_ITERATIONS = 10;
+constexpr double MAX_LIPSCHITZ_CONSTANT = 1e9;
+constexpr int MAX_LINESEARCH_ITERATIONS = 10;
+constexpr double MIN_L_ESTIMATE = 1e-10;
+// lbfgs settings chosen by PANOCCache::new
+constexpr double CBFGS_EPSILON = 1e-8;
+constexpr double SY_EPSILON = 1e-10;
+
+// per-lane L-BFGS + PANOC state
+struct Lane {
+  double u0, u1;          // current iterate
+  double g0, g1;          // gradient at u (or u_plus during the line search)
+  double gp0, gp1;        // previous gradient (AKKT residual)
+  double h0, h1;          // u_half_step
+  double s0, s1;          // gradient_step
+  double d0, d1;          // L-BFGS direction
+  double f0, f1;          // gamma * fixed point residual
+  double os0, os1, og0, og1;  // lbfgs old_state / old_g
+};
+
+struct Uni {  // warp-uniform scalars
+  double gamma, L, sigma, cost, norm_fpr, tau, akkt_tol, lb_gamma;
+  int iteration, lb_active, lb_head, lb_first;
+};
+
+__device__ __forceinline__ void project(const DevCfg &g, double a0, double a1, double &o0, double &o1) {
+  o0 = clipd(a0, g.vmin, g.vmax);
+  o1 = clipd(a1, -g.wmax, g.wmax);
+}
+
+__device__ __forceinline__ int lb_slot(const DevCfg &g, const Uni &U, int i) {
+  int s = U.lb_head + i;
+  const int m1 = g.mem + 1;
+  return s >= m1 ? s - m1 : s;
+}
+
+// lbfgs::update_hessian(g = fpr, state = u)
+__device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm, Lane &z, Uni &U,
+                                             int lane) {
+  const int N = g.N;
+  if (U.lb_first) {
+    U.lb_first = 0;
+    z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
+    return;
+  }
+  const double sv0 = z.u0 - z.os0, sv1 = z.u1 - z.os1;
+  const double yv0 = z.f0 - z.og0, yv1 = z.f1 - z.og1;
+  double ys = sv0 * yv0 + sv1 * yv1, ss = sv0 * sv0 + sv1 * sv1, yy = yv0 * yv0 + yv1 * yv1;
+  wsum3(ys, ss, yy);
+  const double rho = 1.0 / ys;
+  if (ss <= 2.2250738585072014e-308 || ys <= SY_EPSILON) return;
+  {
+    const double lhs = ys / ss;
+    const double rhs = CBFGS_EPSILON * U.norm_fpr;  // cbfgs_alpha = 1: pow(x, 1) == x
+    if (!(lhs > rhs && isfinite(lhs) && isfinite(rhs))) return;
+  }
+  z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
+  // rotate_right(1): scratch slot becomes slot 0
+  U.lb_head = U.lb_head + g.mem; if (U.lb_head >= g.mem + 1) U.lb_head -= g.mem + 1;
+  const int k0 = U.lb_head;
+  if (lane < N) {
+    sm.lbs[k0 * N + lane] = make_double2(sv0, sv1);
+    sm.lby[k0 * N + lane] = make_double2(yv0, yv1);
+  }
+  if (lane == 0) sm.rho[k0] = rho;
+  U.lb_gamma = (1.0 / rho) / yy;
+  U.lb_active = min(g.mem, U.lb_active + 1);
+  __syncwarp();
+}
+
+// lbfgs::apply_hessian on the direction (two-loop recursion)
+__device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm, Lane &z,
+                                            const Uni &U, int lane) {
+  if (U.lb_active == 0) return;
+  const int N = g.N;
+  const bool act = lane < N;
+  double q0 = z.d0, q1 = z.d1;
+  for (int i = 0; i < U.lb_active; i++) {
+    const int k = lb_slot(g, U, i);
+    const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
+    const double2 y = act ? sm.lby[k * N + lane] : make_double2(0.0, 0.0);
+    const double a = sm.rho[k] * wsum(s.x * q0 + s.y * q1);
+    if (lane == 0) sm.alpha[i] = a;
+    q0 += -a * y.x; q1 += -a * y.y;
+  }
+  __syncwarp();
+  q0 *= U.lb_gamma; q1 *= U.lb_gamma;
+  for (int i = U.lb_active - 1; i >= 0; i--) {
+    const int k = lb_slot(g, U, i);
+    const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
+    const double2 y = act ? sm.lby[k * N + lane] : make_double2(0.0, 0.0);
+    const double beta = sm.rho[k] * wsum(y.x * q0 + y.y * q1);
+    const double cf = sm.alpha[i] - beta;
+    q0 += cf * s.x; q1 += cf * s.y;
+  }
+  z.d0 = q0; z.d1 = q1;
+}
+
+struct Problem {  // what eval needs besides the point
+  double c, ya, yw;
+};
+
+__device__ __forceinline__ double eval_cost(const DevCfg &g, const WarpSmem &sm, int lane,
+                                            const Problem &pb, double a0, double a1) {
+  EvalOut e = eval_psi<false>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                              pb.yw, nullptr);
+  if (lane == 0) sm.ctx->n_cost++;
+  return e.psi;
+}
+__device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm, int lane,
+                                            const Problem &pb, double a0, double a1, double &o0,
+                                            double &o1) {
+  EvalOut e = eval_psi<true>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                             pb.yw, nullptr);
+  if (lane == 0) sm.ctx->n_grad++;
+  o0 = e.gv; o1 = e.gw;
+  return e.psi;
+}
+
+__device__ __forceinline__ void compute_fpr(Lane &z, Uni &U) {
+  z.f0 = z.u0 - z.h0; z.f1 = z.u1 - z.h1;
+  U.norm_fpr = sqrt(wsum(z.f0 * z.f0 + z.f1 * z.f1));
+}
+__device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z, const Uni &U,
+                                                       double a0, double a1) {
+  z.s0 = a0 - U.gamma * z.g0; z.s1 = a1 - U.gamma * z.g1;
+  project(g, z.s0, z.s1, z.h0, z.h1);
+}
+
+// PANOCEngine::step.  Returns true to continue.
+__device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, int lane, const Problem &pb,
+                           Lane &z, Uni &U, double tolerance) {
+  if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
+  compute_fpr(z, U);
+  if (U.norm_fpr < tolerance) {
+    const double r0 = z.f0 + U.gamma * (z.g0 - z.gp0), r1 = z.f1 + U.gamma * (z.g1 - z.gp1);
+    if (sqrt(wsum(r0 * r0 + r1 * r1)) < U.akkt_tol) return false;
+  }
+  // update_lipschitz_constant
+  {
+    double cost_half = eval_cost(g, sm, lane, pb, z.h0, z.h1);
+    int it = 0;
+    while (true) {
+      const double ip = wsum(z.g0 * z.f0 + z.g1 * z.f1);
+      const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - ip +
+                         (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
+      if (!(cost_half > rhs && it < MAX_LIPSCHITZ_UPDATE_ITERATIONS &&
+            U.L < MAX_LIPSCHITZ_CONSTANT))
+        break;
+      U.lb_active = 0; U.lb_first = 1;  // lbfgs.reset()
+      U.L *= 2.0;
+      U.gamma /= 2.0;
+      gradient_and_half_step(g, z, U, z.u0, z.u1);
+      cost_half = eval_cost(g, sm, lane, pb, z.h0, z.h1);
+      compute_fpr(z, U);
+      it++;
+    }
+    U.sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * U.gamma);
+  }
+  // lbfgs_direction
+  lbfgs_update(g, sm, z, U, lane);
+  if (U.iteration > 0) {
+    z.d0 = z.f0; z.d1 = z.f1;
+    lbfgs_apply(g, sm, z, U, lane);
+  }
+  if (U.iteration == 0) {
+    // update_no_linesearch
+    z.u0 = z.h0; z.u1 = z.h1;
+    U.cost = eval_grad(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
+    gradient_and_half_step(g, z, U, z.u0, z.u1);
+  } else {
+    // linesearch on the forward-backward envelope
+    const double e0 = z.s0 - z.h0, e1 = z.s1 - z.h1;
+    double dist2 = e0 * e0 + e1 * e1, gg = z.g0 * z.g0 + z.g1 * z.g1, dummy = 0.0;
+    wsum3(dist2, gg, dummy);
+    const double fbe = U.cost - 0.5 * U.gamma * gg + 0.5 * dist2 / U.gamma;
+    const double rhs_ls = fbe - U.sigma * (U.norm_fpr * U.norm_fpr);
+    U.tau = 1.0;
+    int nls = 0;
+    double p0, p1;
+    while (true) {
+      const double one_m = 1.0 - U.tau;
+      p0 = z.u0 - one_m * z.f0 - U.tau * z.d0;
+      p1 = z.u1 - one_m * z.f1 - U.tau * z.d1;
+      U.cost = eval_grad(g, sm, lane, pb, p0, p1, z.g0, z.g1);
+      gradient_and_half_step(g, z, U, p0, p1);
+      const double q0 = z.h0 - z.s0, q1 = z.h1 - z.s1;
+      double dd = q0 * q0 + q1 * q1, g2 = z.g0 * z.g0 + z.g1 * z.g1, dm = 0.0;
+      wsum3(dd, g2, dm);
+      const double lhs_ls = U.cost - 0.5 * U.gamma * g2 + 0.5 * dd / U.gamma;
+      if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
+      U.tau /= 2.0;
+      nls++;
+    }
+    z.u0 = p0; z.u1 = p1;
+  }
+  U.iteration++;
+  return true;
+}
+
+__device__ __forceinline__ void panoc_reset(Uni &U) {
+  U.lb_active = 0; U.lb_first = 1;
+  U.tau = 1.0; U.L = 0.0; U.sigma = 0.0; U.cost = 0.0; U.iteration = 0; U.gamma = 0.0;
+}
+
+// One scene, start to finish.
+__device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs &A, int scene,
+                            int lane, unsigned long long *wstats) {
+  const int N = g.N;
+  const bool act = lane < N;
+  Lane z;
+  Uni U;
+  Problem pb;
+  z.u0 = z.u1 = 0.0;
+  pb.ya = pb.yw = 0.0;
+  if (act) {
+    if (A.use_u0) {
+      z.u0 = A.u[(size_t)scene * 2 * N + 2 * lane];
+      z.u1 = A.u[(size_t)scene * 2 * N + 2 * lane + 1];
+    }
+    if (A.use_y0 && A.y) {
+      pb.ya = A.y[(size_t)scene * 2 * N + lane];
+      pb.yw = A.y[(size_t)scene * 2 * N + N + lane];
+    }
+  }
+  pb.c = A.c0 ? A.c0[scene] : g.c0;
+  z.g0 = z.g1 = z.gp0 = z.gp1 = z.h0 = z.h1 = z.s0 = z.s1 = 0.0;
+  z.d0 = z.d1 = z.f0 = z.f1 = z.os0 = z.os1 = z.og0 = z.og1 = 0.0;
+  U.lb_head = 0; U.lb_gamma = 1.0; U.norm_fpr = 0.0;
+  panoc_reset(U);
+  U.akkt_tol = g.init_tol;
+
+  double yp_a = 0.0, yp_w = 0.0;  // y_plus
+  double delta_y_norm = 0.0, delta_y_norm_plus = 0.0, f2_norm = 0.0, f2_norm_plus = 0.0;
+  double last_fpr = 0.0, f_final = 0.0;
+  int alm_iter = 0, inner_count = 0, num_outer = 0, exit_status = TTMPC_CONVERGED;
+  unsigned long long panoc_iters = 0;
+  const double SMALL_EPSILON = 2.220446049250313e-16;
+
+  for (int outer = 1; outer <= g.max_outer; outer++) {
+    num_outer++;
+    pb.ya = clipd(pb.ya, -1e12, 1e12);
+    pb.yw = clipd(pb.yw, -1e12, 1e12);
+    // ---------------- inner problem: PANOCOptimizer::solve
+    int inner_status;
+    {
+      panoc_reset(U);
+      // init: cost, gradient, local Lipschitz estimate
+      U.cost = eval_grad(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
+      if (lane == 0) sm.ctx->n_cost++;  // the reference evaluates cost and gradient separately
+      {
+        double h0 = 0.0, h1 = 0.0;
+        if (act) {
+          h0 = (EPSILON_LIPSCHITZ * z.u0 > DELTA_LIPSCHITZ) ? EPSILON_LIPSCHITZ * z.u0 : DELTA_LIPSCHITZ;
+          h1 = (EPSILON_LIPSCHITZ * z.u1 > DELTA_LIPSCHITZ) ? EPSILON_LIPSCHITZ * z.u1 : DELTA_LIPSCHITZ;
+        }
+        double t0, t1;
+        eval_grad(g, sm, lane, pb, z.u0 + h0, z.u1 + h1, t0, t1);
+        double nh = h0 * h0 + h1 * h1;
+        double nd = (t0 - z.g0) * (t0 - z.g0) + (t1 - z.g1) * (t1 - z.g1);
+        double dm = 0.0;
+        wsum3(nh, nd, dm);
+        U.L = sqrt(nd) / sqrt(nh);
+      }
+      U.gamma = GAMMA_L_COEFF / fmax(U.L, MIN_L_ESTIMATE);
+      U.sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * U.gamma);
+      gradient_and_half_step(g, z, U, z.u0, z.u1);
+
+      // PANOCOptimizer::solve main loop (one call site: step, then count)
+      int num_iter = 0;
+      bool cont = true;
+      while (true) {
+        const bool flag = panoc_step(g, sm, lane, pb, z, U, g.tol);
+        if (!(flag && cont)) break;
+        num_iter++;
+        cont = num_iter < g.max_inner;
+      }
+      const bool finite = isfinite(z.u0) && isfinite(z.u1);
+      if (!__all_sync(FULL, finite)) { exit_status = TTMPC_NOT_FINITE; inner_count += num_iter; break; }
+      z.u0 = z.h0; z.u1 = z.h1;
+      inner_status = cont ? TTMPC_CONVERGED : TTMPC_NOT_CONVERGED_ITERATIONS;
+      inner_count += num_iter;
+      panoc_iters += num_iter;
+      last_fpr = U.norm_fpr;
+    }
+    // ---------------- multipliers, infeasibility (alm_optimizer.rs step())
+    double F1a = 0.0, F1w = 0.0;
+    {
+      double vp = __shfl_up_sync(FULL, z.u0, 1), wp = __shfl_up_sync(FULL, z.u1, 1);
+      if (lane == 0) { vp = sm.ctx->v_init; wp = sm.ctx->w_init; }
+      if (act) { F1a = (z.u0 - vp) / g.ts; F1w = (z.u1 - wp) / g.ts; }
+    }
+    {
+      const double cm = fmax(pb.c, 1.0);
+      double t = clipd(F1a + pb.ya / cm, g.amin, g.amax);
+      yp_a = pb.ya + pb.c * (F1a - t);
+      t = clipd(F1w + pb.yw / cm, -g.awmax, g.awmax);
+      yp_w = pb.yw + pb.c * (F1w - t);
+      if (!act) { yp_a = 0.0; yp_w = 0.0; }
+    }
+    {
+      EvalOut e = eval_psi<false>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0,
+                                  0.0, 0.0, nullptr);
+      if (lane == 0) sm.ctx->n_cost++;
+      f2_norm_plus = sqrt(e.f2sq);
+      f_final = e.f;
+    }
+    {
+      const double da = yp_a - pb.ya, dw = yp_w - pb.yw;
+      delta_y_norm_plus = sqrt(wsum(da * da + dw * dw));
+    }
+    const bool crit1 = alm_iter > 0 && delta_y_norm_plus <= pb.c * g.delta_tol + SMALL_EPSILON;
+    const bool crit2 = f2_norm_plus <= g.delta_tol + SMALL_EPSILON;
+    const bool crit3 = U.akkt_tol <= g.tol + SMALL_EPSILON;
+    if (crit1 && crit2 && crit3) { exit_status = inner_status; break; }
+    const bool stall = alm_iter == 0 ||
+                       delta_y_norm_plus <= g.suff_dec * delta_y_norm + SMALL_EPSILON ||
+                       f2_norm_plus <= g.suff_dec * f2_norm + SMALL_EPSILON;
+    if (!stall) pb.c *= g.pen_factor;
+    U.akkt_tol = fmax(U.akkt_tol * g.tol_factor, g.tol);
+    z.gp0 = 0.0; z.gp1 = 0.0;  // set_akkt_tolerance allocates a fresh zero vector
+    alm_iter++;
+    delta_y_norm = delta_y_norm_plus;
+    f2_norm = f2_norm_plus;
+    pb.ya = yp_a; pb.yw = yp_w;
+  }
+  if (exit_status != TTMPC_NOT_FINITE && num_outer == g.max_outer)
+    exit_status = TTMPC_NOT_CONVERGED_ITERATIONS;
+
+  // ---------------- results
+  if (act) {
+    A.u[(size_t)scene * 2 * N + 2 * lane] = z.u0;
+    A.u[(size_t)scene * 2 * N + 2 * lane + 1] = z.u1;
+    if (A.y) {
+      A.y[(size_t)scene * 2 * N + lane] = pb.ya;
+      A.y[(size_t)scene * 2 * N + N + lane] = pb.yw;
+    }
+  }
+  if (A.pred_states) {
+    eval_psi<false>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0, 0.0,
+                    A.pred_states + (size_t)scene * N * 3);
+  }
+  if (lane == 0) {
+    if (A.cost) A.cost[scene] = f_final;
+    if (A.exit_status) A.exit_status[scene] = exit_status;
+    if (A.outer_iters) A.outer_iters[scene] = num_outer;
+    if (A.inner_iters) A.inner_iters[scene] = inner_count;
+    if (A.last_fpr) A.last_fpr[scene] = last_fpr;
+    if (A.f1_infeas) A.f1_infeas[scene] = delta_y_norm_plus / pb.c;
+    if (A.f2_norm) A.f2_norm[scene] = f2_norm_plus;
+    if (A.penalty) A.penalty[scene] = pb.c;
+    if (A.evals) { A.evals[2 * scene] = sm.ctx->n_cost; A.evals[2 * scene + 1] = sm.ctx->n_grad; }
+    wstats[0] += sm.ctx->n_cost;
+    wstats[1] += sm.ctx->n_grad;
+    wstats[2] += sm.ctx->n_body;
+    wstats[3] += panoc_iters;
+  }
+}
+
+__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevCfg g,
+                                                    const __grid_constant__ SolveArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WarpSmem sm = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
+  const int gwarp = blockIdx.x * g.warps_per_block + warp;
+  double *dyn = A.dyn_scratch + (size_t)gwarp * DYN_FIELDS * g.Ndyn * g.N;
+  unsigned long long wstats[4] = {0, 0, 0, 0};
+  while (true) {
+    int scene = 0;
+    if (lane == 0) scene = atomicAdd(A.work_counter, 1);
+    scene = __shfl_sync(FULL, scene, 0);
+    if (scene >= A.n_scenes) break;
+    stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
+    solve_scene(g, sm, A, scene, lane, wstats);
+    __syncwarp();
+  }
+  if (lane == 0 && A.stats) {
+    for (int i = 0; i < 4; i++)
+      if (wstats[i]) atomicAdd(A.stats + i, wstats[i]);
+  }
+}
+
+// ------------------------------------------------------------------ batched evaluation
+__global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevCfg g,
+                                                   const __grid_constant__ EvalArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WarpSmem sm = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
+  const int gwarp = blockIdx.x * g.warps_per_block + warp;
+  const int nwarps = gridDim.x * g.warps_per_block;
+  double *dyn = A.dyn_scratch + (size_t)gwarp * DYN_FIELDS * g.Ndyn * g.N;
+  const int N = g.N;
+  for (int scene = gwarp; scene < A.n_scenes; scene += nwarps) {
+    stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
+    const bool act = lane < N;
+    double v = 0.0, w = 0.0, ya = 0.0, yw = 0.0;
+    if (act) {
+      v = A.u[(size_t)scene * 2 * N + 2 * lane];
+      w = A.u[(size_t)scene * 2 * N + 2 * lane + 1];
+      if (A.y) { ya = A.y[(size_t)scene * 2 * N + lane]; yw = A.y[(size_t)scene * 2 * N + N + lane]; }
+    }
+    const double c = A.c ? A.c[scene] : 0.0;
+    EvalOut e = eval_psi<true>(&g, reinterpret_cast<unsigned char *>(sm.ctx), v, w, c, ya, yw, nullptr);
+    const double gv = e.gv, gw = e.gw;
+    double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
+    if (lane == 0) { vp = sm.ctx->v_init; wp = sm.ctx->w_init; }
+    if (act) {
+      if (A.grad) { A.grad[(size_t)scene * 2 * N + 2 * lane] = gv; A.grad[(size_t)scene * 2 * N + 2 * lane + 1] = gw; }
+      if (A.F1) {
+        A.F1[(size_t)scene * 2 * N + lane] = (v - vp) / g.ts;
+        A.F1[(size_t)scene * 2 * N + N + lane] = (w - wp) / g.ts;
+      }
+    }
+    if (A.F2)
+      for (int j = lane; j < g.Ndyn; j += 32) A.F2[(size_t)scene * g.Ndyn + j] = e.S + sm.D[j];
+    if (lane == 0) {
+      if (A.f) A.f[scene] = e.f;
+      if (A.psi) A.psi[scene] = e.psi;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ FP64 peak probe
+__global__ void fp64_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace ttmpc
+
+// ------------------------------------------------------------------ launch helpers (host)
+namespace ttmpc {
+
+cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  solve_kernel<<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  return cudaGetLastError();
+}
+cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  cudaError_t e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  eval_kernel<<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  return cudaGetLastError();
+}
+cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm) {
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel,
+                                                       g.warps_per_block * 32, smem);
+}
+cudaError_t launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t st) {
+  fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace ttmpc
