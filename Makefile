@@ -3,7 +3,7 @@ NVCC      ?= nvcc
 CC        ?= gcc
 PKG       := trajtrack_mpcndqn_rlboost_b200
 CSRC      := $(PKG)/csrc
-NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
              -Xcompiler -fPIC -Xcompiler -O2
 LIB       := $(PKG)/libttmpc.so
 ORACLE    := oracle/libttmpc_oracle.so

@@ -384,6 +384,370 @@ void ttmpc_oracle_rollout(const ttmpc_config *g, const double *u, const double *
 }
 
 /* ------------------------------------------------------------------ */
+/* Part 1b: WARP-ordered evaluation                                    */
+/*                                                                     */
+/* Same functions as Part 1, evaluated with the operation order of the */
+/* CUDA kernel (csrc/ttmpc_device.cuh): 32 lanes, lane k owns step k,  */
+/* Kogge-Stone prefix/suffix scans for the rollout and its adjoint,    */
+/* butterfly all-reduces, explicit fma(), and tt_sincos instead of     */
+/* libm.  Compiled with -ffp-contract=off this reproduces the GPU      */
+/* arithmetic bit for bit; tests check it against Part 1 (1e-12) and   */
+/* against the GPU (exact).                                            */
+/* ------------------------------------------------------------------ */
+
+static void tt_sincos(double x, double *s, double *c) {
+  if (!(fabs(x) < 1.0e9)) { *s = x * 0.0 + NAN; *c = *s; return; }
+  const double kd = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-kd, 1.5707963267948966e+00, x);
+  r = fma(-kd, 6.123233995736766e-17, r);
+  r = fma(-kd, -1.4973849048591698e-33, r);
+  const int q = (int)((long long)kd & 3);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  switch (q) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+  }
+}
+void ttmpc_oracle_sincos(double x, double *s, double *c) { tt_sincos(x, s, c); }
+
+#define WL 32
+static double w_sum(const double *v) { /* butterfly all-reduce, offsets 16..1 */
+  double a[WL], b[WL];
+  memcpy(a, v, sizeof(a));
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int i = 0; i < WL; i++) b[i] = a[i] + a[i ^ o];
+    memcpy(a, b, sizeof(a));
+  }
+  return a[0];
+}
+static void w_scan(double *v) { /* inclusive Kogge-Stone prefix sum */
+  double b[WL];
+  for (int o = 1; o < WL; o <<= 1) {
+    for (int i = 0; i < WL; i++) b[i] = (i >= o) ? v[i] + v[i - o] : v[i];
+    memcpy(v, b, sizeof(b));
+  }
+}
+static void w_suffix(double *v) { /* inclusive suffix sum */
+  double b[WL];
+  for (int o = 1; o < WL; o <<= 1) {
+    for (int i = 0; i < WL; i++) b[i] = (i + o < WL) ? v[i] + v[i + o] : v[i];
+    memcpy(v, b, sizeof(b));
+  }
+}
+static double pdot(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
+
+typedef struct { /* what stage_scene builds on the device */
+  double seg[5][MAXN];
+  double os[64 * 3 * MAXEDGE];
+  double dyn[10][MAXDYN][MAXN];
+  double D[MAXDYN];
+  long long n_body;
+} wstage_t;
+
+static void w_stage(const ttmpc_config *g, const double *p, wstage_t *W) {
+  const offs_t o = offsets(g);
+  const int N = g->N_hor, ne = g->nstcobs / 3;
+  const double *r = p + o.r, *os = p + o.os, *od = p + o.od, *qdyn = p + o.qdyn;
+  for (int j = 0; j < N; j++) {
+    int j2 = (j + 1 < N) ? j + 1 : N - 1;
+    double s1x = r[3 * j], s1y = r[3 * j + 1];
+    double sx = r[3 * j2] - s1x, sy = r[3 * j2 + 1] - s1y;
+    double den = fma(sy, sy, sx * sx) + 1e-16;
+    W->seg[0][j] = s1x; W->seg[1][j] = s1y; W->seg[2][j] = sx; W->seg[3][j] = sy;
+    W->seg[4][j] = 1.0 / den;
+  }
+  for (int i = 0; i < g->Nstcobs * g->nstcobs; i++) {
+    int e = i % g->nstcobs;
+    W->os[i] = (e < ne) ? os[i] : -os[i];
+  }
+  for (int j = 0; j < g->Ndynobs; j++)
+    for (int k = 0; k < N; k++) {
+      const double *e = od + ((size_t)j * N + k) * 6;
+      double cx = e[0], cy = e[1], rx = e[2], ry = e[3], ang = e[4], alpha = e[5];
+      double sa, ca;
+      tt_sincos(ang, &sa, &ca);
+      double Rx = rx + 1e-6, Ry = ry + 1e-6;
+      double Rxm = rx + g->social_margin + 1e-6, Rym = ry + g->social_margin + 1e-6;
+      double rmax = fmax(fmax(fabs(Rx), fabs(Ry)), fmax(fabs(Rxm), fabs(Rym)));
+      W->dyn[0][j][k] = cx; W->dyn[1][j][k] = cy;
+      W->dyn[2][j][k] = rmax * rmax * (1.0 + 1e-9);
+      W->dyn[3][j][k] = ca; W->dyn[4][j][k] = sa;
+      W->dyn[5][j][k] = 1.0 / (Rx * Rx); W->dyn[6][j][k] = 1.0 / (Ry * Ry);
+      W->dyn[7][j][k] = 1.0 / (Rxm * Rxm); W->dyn[8][j][k] = 1.0 / (Rym * Rym);
+      W->dyn[9][j][k] = alpha * qdyn[k];
+    }
+  W->n_body = 0;
+}
+
+typedef struct { double psi, f, f2sq, S; } wout_t;
+
+/* mirror of eval_psi<GRAD> in csrc/ttmpc_device.cuh; u interleaved (v0 w0 v1 w1 ...),
+ * y = [ya_0..ya_{N-1}, yw_0..yw_{N-1}] (may be NULL), grad interleaved or NULL */
+static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const double *u,
+                     double c, const double *y, double *grad, double *st_out) {
+  const offs_t o = offsets(g);
+  const int N = g->N_hor, ne = g->nstcobs / 3, GRAD = grad != NULL;
+  const double ts = g->ts, h6 = g->ts / 6.0, veh_d2 = g->vehicle_width * g->vehicle_width;
+  const double *s = p + o.s, *q = p + o.q;
+  const double x0 = s[0], y0 = s[1], th0 = s[2], xg = s[3], yg = s[4], thg = s[5];
+  const double v_init = s[6], w_init = s[7];
+  const double qvel = q[1], rv = q[3], rw = q[4], qN = q[5], qthetaN = q[6], qrpd = q[7],
+               acc_pen = q[8], wacc_pen = q[9];
+  double v[WL], w[WL], tw[WL], th_in[WL], sa[WL], ca[WL], sb[WL], cb[WL], sc[WL], cc[WL];
+  double Cs[WL], Ss[WL], hv[WL], dx[WL], dy[WL], X[WL], Y[WL], TH[WL];
+  double cost[WL], gx[WL], gy[WL], gt[WL], S_loc[WL], gSx[WL], gSy[WL];
+  double aa[WL], aw[WL], ea[WL], ew[WL], alm[WL], vr[WL];
+  for (int k = 0; k < WL; k++) {
+    v[k] = k < N ? u[2 * k] : 0.0;
+    w[k] = k < N ? u[2 * k + 1] : 0.0;
+    tw[k] = ts * w[k];
+    th_in[k] = tw[k];
+    cost[k] = gx[k] = gy[k] = gt[k] = S_loc[k] = gSx[k] = gSy[k] = 0.0;
+    aa[k] = aw[k] = ea[k] = ew[k] = alm[k] = vr[k] = 0.0;
+  }
+  w_scan(th_in);
+  for (int k = 0; k < WL; k++) {
+    double th_ex = k ? th_in[k - 1] : 0.0;
+    double tha = th0 + th_ex;
+    double thb = fma(0.5, tw[k], tha), thc = tha + tw[k];
+    tt_sincos(tha, &sa[k], &ca[k]);
+    tt_sincos(thb, &sb[k], &cb[k]);
+    tt_sincos(thc, &sc[k], &cc[k]);
+    Cs[k] = fma(4.0, cb[k], ca[k]) + cc[k];
+    Ss[k] = fma(4.0, sb[k], sa[k]) + sc[k];
+    hv[k] = h6 * v[k];
+    dx[k] = hv[k] * Cs[k]; dy[k] = hv[k] * Ss[k];
+    X[k] = dx[k]; Y[k] = dy[k];
+  }
+  w_scan(X); w_scan(Y);
+  for (int k = 0; k < WL; k++) { X[k] = x0 + X[k]; Y[k] = y0 + Y[k]; TH[k] = th0 + th_in[k]; }
+  if (st_out)
+    for (int k = 0; k < N; k++) { st_out[3 * k] = X[k]; st_out[3 * k + 1] = Y[k]; st_out[3 * k + 2] = TH[k]; }
+
+  unsigned long long hard_mask = 0;
+  for (int j = 0; j < g->Ndynobs; j++) W->D[j] = 0.0;
+  double in1_all[MAXDYN][WL];
+  for (int k = 0; k < N; k++) { /* per-lane work, lanes are independent here */
+    /* reference path */
+    double dmin = 0.0; int jmin = k;
+    for (int j = k; j < N; j++) {
+      const double s1x = W->seg[0][j], s1y = W->seg[1][j], sx = W->seg[2][j], sy = W->seg[3][j],
+                   inv = W->seg[4][j];
+      const double px = X[k] - s1x, py = Y[k] - s1y;
+      const double t_hat = fma(py, sy, px * sx) * inv;
+      const double t = fmin(fmax(t_hat, 0.0), 1.0);
+      const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
+      const double d2 = fma(qy, qy, qx * qx);
+      if (j == k || !(dmin <= d2)) { dmin = d2; jmin = j; }
+    }
+    cost[k] = dmin * qrpd;
+    if (GRAD) {
+      const int j = jmin;
+      const double s1x = W->seg[0][j], s1y = W->seg[1][j], sx = W->seg[2][j], sy = W->seg[3][j],
+                   inv = W->seg[4][j];
+      const double px = X[k] - s1x, py = Y[k] - s1y;
+      const double t_hat = fma(py, sy, px * sx) * inv;
+      const double t = fmin(fmax(t_hat, 0.0), 1.0);
+      const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
+      const double pass = (t_hat >= 0.0 && t_hat <= 1.0) ? 1.0 : 0.0;
+      const double cs = fma(qy, sy, qx * sx) * pass * inv;
+      gx[k] = qrpd * (2.0 * fma(cs, sx, -qx));
+      gy[k] = qrpd * (2.0 * fma(cs, sy, -qy));
+    }
+    /* speed reference + control action */
+    vr[k] = p[o.vref + k];
+    {
+      const double dv_ = v[k] - vr[k];
+      cost[k] += qvel * (dv_ * dv_);
+      cost[k] += fma(rw, w[k] * w[k], rv * (v[k] * v[k]));
+    }
+    /* fleet */
+    {
+      const double *cp = p + o.c + 3 * k;
+      double acc = 0.0, fx = 0.0, fy = 0.0;
+      for (int j = 0; j < g->Nother; j++) {
+        const double ox = cp[(size_t)j * 3 * N], oy = cp[(size_t)j * 3 * N + 1];
+        const double ex = X[k] - ox, ey = Y[k] - oy;
+        const double e = veh_d2 - fma(ey, ey, ex * ex);
+        if (e > 0.0) {
+          acc += e;
+          if (GRAD) { fx = fma(-2.0, ex, fx); fy = fma(-2.0, ey, fy); }
+        }
+      }
+      cost[k] += 1000.0 * acc;
+      if (GRAD) { gx[k] = fma(1000.0, fx, gx[k]); gy[k] = fma(1000.0, fy, gy[k]); }
+    }
+    /* dynamic obstacles */
+    {
+      double soft = 0.0;
+      for (int j = 0; j < g->Ndynobs; j++) {
+        const double ex = X[k] - W->dyn[0][j][k], ey = Y[k] - W->dyn[1][j][k];
+        const int pass = fma(ey, ey, ex * ex) < W->dyn[2][j][k];
+        double in1 = 0.0;
+        if (pass) {
+          W->n_body++;
+          const double ca_ = W->dyn[3][j][k], sa_ = W->dyn[4][j][k];
+          const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
+          const double A2 = A * A, B2 = B * B;
+          in1 = fma(-B2, W->dyn[6][j][k], fma(-A2, W->dyn[5][j][k], 1.0));
+          const double iRxm = W->dyn[7][j][k], iRym = W->dyn[8][j][k];
+          const double in2 = fma(-B2, iRym, fma(-A2, iRxm, 1.0));
+          if (in2 > 0.0) {
+            const double ws = W->dyn[9][j][k];
+            soft = fma(in2 * in2, ws, soft);
+            if (GRAD) {
+              const double wg = ws * (2.0 * in2);
+              const double tA = A * iRxm, tB = B * iRym;
+              gx[k] = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx[k]);
+              gy[k] = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy[k]);
+            }
+          }
+        }
+        in1_all[j][k] = in1 > 0.0 ? in1 : 0.0;
+        if (in1 > 0.0) hard_mask |= 1ull << j;
+      }
+      cost[k] += soft;
+    }
+    /* terminal */
+    if (k == N - 1) {
+      const double dxg = X[k] - xg, dyg = Y[k] - yg, dtg = TH[k] - thg;
+      cost[k] += fma(qthetaN, dtg * dtg, qN * fma(dyg, dyg, dxg * dxg));
+      if (GRAD) {
+        gx[k] = fma(2.0 * qN, dxg, gx[k]);
+        gy[k] = fma(2.0 * qN, dyg, gy[k]);
+        gt[k] = 2.0 * qthetaN * dtg;
+      }
+    }
+    /* static obstacles */
+    for (int i = 0; i < g->Nstcobs; i++) {
+      const double *b = W->os + i * g->nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
+      double m[MAXEDGE], sq[MAXEDGE], inside = 1.0;
+      for (int e = 0; e < ne; e++) {
+        const double res = fma(na1[e], Y[k], fma(na0[e], X[k], b[e]));
+        m[e] = fmax(0.0, res);
+        sq[e] = m[e] * m[e];
+        inside *= sq[e];
+      }
+      if (inside > 0.0) {
+        S_loc[k] += inside;
+        if (GRAD)
+          for (int e = 0; e < ne; e++) {
+            double rest = 1.0;
+            for (int e2 = 0; e2 < ne; e2++) if (e2 != e) rest *= sq[e2];
+            const double coef = rest * (2.0 * m[e]);
+            gSx[k] = fma(coef, na0[e], gSx[k]);
+            gSy[k] = fma(coef, na1[e], gSy[k]);
+          }
+      }
+    }
+    /* accelerations + ALM */
+    {
+      const double vp = k ? v[k - 1] : v_init, wp = k ? w[k - 1] : w_init;
+      aa[k] = (v[k] - vp) / ts; aw[k] = (w[k] - wp) / ts;
+      cost[k] += fma(aw[k] * aw[k], wacc_pen, (aa[k] * aa[k]) * acc_pen);
+      const double cm = fmax(c, 1.0);
+      double z = aa[k] + (y ? y[k] : 0.0) / cm;
+      ea[k] = z - clip(z, g->lin_acc_min, g->lin_acc_max);
+      z = aw[k] + (y ? y[N + k] : 0.0) / cm;
+      ew[k] = z - clip(z, -g->ang_acc_max, g->ang_acc_max);
+      alm[k] = fma(ew[k], ew[k], ea[k] * ea[k]);
+    }
+  }
+  /* D_j: butterfly sum over lanes, only for obstacles with a positive term */
+  for (int j = 0; j < g->Ndynobs; j++)
+    if (hard_mask >> j & 1ull) {
+      double t[WL];
+      for (int k = 0; k < WL; k++) t[k] = k < N ? in1_all[j][k] : 0.0;
+      W->D[j] = w_sum(t);
+    }
+  const double f = w_sum(cost), d2 = w_sum(alm), S = w_sum(S_loc);
+  double f2sq = 0.0, sumF2 = 0.0;
+  for (int j = 0; j < g->Ndynobs; j++) {
+    const double F2j = S + W->D[j];
+    f2sq = fma(F2j, F2j, f2sq);
+    sumF2 += F2j;
+  }
+  wout_t out;
+  out.f = f; out.f2sq = f2sq; out.S = S;
+  out.psi = f + c * d2 / 2 + c * f2sq / 2;
+  if (GRAD) {
+    if (c != 0.0) {
+      const double cs_ = c * sumF2;
+      for (int k = 0; k < N; k++) {
+        gx[k] = fma(cs_, gSx[k], gx[k]);
+        gy[k] = fma(cs_, gSy[k], gy[k]);
+        for (int j = 0; j < g->Ndynobs; j++) {
+          if (!(hard_mask >> j & 1ull)) continue;
+          const double ex = X[k] - W->dyn[0][j][k], ey = Y[k] - W->dyn[1][j][k];
+          if (fma(ey, ey, ex * ex) < W->dyn[2][j][k]) {
+            const double ca_ = W->dyn[3][j][k], sa_ = W->dyn[4][j][k];
+            const double iRx = W->dyn[5][j][k], iRy = W->dyn[6][j][k];
+            const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
+            const double in1 = fma(-(B * B), iRy, fma(-(A * A), iRx, 1.0));
+            if (in1 > 0.0) {
+              const double wg = c * (S + W->D[j]);
+              const double tA = A * iRx, tB = B * iRy;
+              gx[k] = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx[k]);
+              gy[k] = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy[k]);
+            }
+          }
+        }
+      }
+    }
+    double lx[WL], ly[WL], m[WL], lt[WL];
+    memcpy(lx, gx, sizeof(lx)); memcpy(ly, gy, sizeof(ly));
+    w_suffix(lx); w_suffix(ly);
+    for (int k = 0; k < WL; k++) {
+      m[k] = fma(ly[k], dx[k], -(lx[k] * dy[k]));
+      lt[k] = gt[k] + m[k];
+    }
+    w_suffix(lt);
+    for (int k = 0; k < WL; k++) lt[k] = lt[k] - m[k];
+    for (int k = 0; k < N; k++) {
+      const double dxdv = h6 * Cs[k], dydv = h6 * Ss[k];
+      const double hvt = hv[k] * ts;
+      const double dxdw = -(hvt * fma(2.0, sb[k], sc[k])), dydw = hvt * fma(2.0, cb[k], cc[k]);
+      const int last = k == N - 1;
+      const double aa_n = last ? 0.0 : aa[k + 1], aw_n = last ? 0.0 : aw[k + 1];
+      const double ea_n = last ? 0.0 : ea[k + 1], ew_n = last ? 0.0 : ew[k + 1];
+      double dv = 2 * qvel * (v[k] - vr[k]) + 2 * rv * v[k];
+      double dw = 2 * rw * w[k];
+      dv += 2 * acc_pen * (aa[k] - aa_n) / ts + c * (ea[k] - ea_n) / ts;
+      dw += 2 * wacc_pen * (aw[k] - aw_n) / ts + c * (ew[k] - ew_n) / ts;
+      grad[2 * k] = dv + lx[k] * dxdv + ly[k] * dydv;
+      grad[2 * k + 1] = dw + lx[k] * dxdw + ly[k] * dydw + lt[k] * ts;
+    }
+  }
+  return out;
+}
+
+/* public: warp-ordered evaluation (testing) */
+void ttmpc_oracle_eval_warp(const ttmpc_config *g, const double *u, const double *p, double c,
+                            const double *y, double *f, double *F2, double *psi, double *grad) {
+  wstage_t *W = (wstage_t *)malloc(sizeof(wstage_t));
+  w_stage(g, p, W);
+  wout_t o = w_eval(g, p, W, u, c, y, grad, NULL);
+  if (f) *f = o.f;
+  if (psi) *psi = o.psi;
+  if (F2) for (int j = 0; j < g->Ndynobs; j++) F2[j] = o.S + W->D[j];
+  free(W);
+}
+
+/* ------------------------------------------------------------------ */
 /* Part 2: OpEn solver restatement (PARITY UNPINNED)                   */
 /* ------------------------------------------------------------------ */
 
@@ -393,14 +757,18 @@ typedef struct {
   double c;        /* xi[0] */
   double *y;       /* xi[1..] */
   long long n_cost, n_grad;
+  int warp;        /* 0: reference order (Part 1, libm)  1: GPU order (Part 1b) */
+  wstage_t *W;
 } prob_t;
 
 static void f_cost(prob_t *pb, const double *u, double *out) {
-  *out = ttmpc_oracle_psi(pb->g, u, pb->p, pb->c, pb->y);
+  if (pb->warp) *out = w_eval(pb->g, pb->p, pb->W, u, pb->c, pb->y, NULL, NULL).psi;
+  else *out = ttmpc_oracle_psi(pb->g, u, pb->p, pb->c, pb->y);
   pb->n_cost++;
 }
 static void f_grad(prob_t *pb, const double *u, double *out) {
-  ttmpc_oracle_psi_grad(pb->g, u, pb->p, pb->c, pb->y, out);
+  if (pb->warp) w_eval(pb->g, pb->p, pb->W, u, pb->c, pb->y, out, NULL);
+  else ttmpc_oracle_psi_grad(pb->g, u, pb->p, pb->c, pb->y, out);
   pb->n_grad++;
 }
 /* og.constraints.Rectangle(umin, umax) (mpc_generator.py:245-247) */
@@ -411,16 +779,23 @@ static void project_u(const ttmpc_config *g, double *u) {
   }
 }
 
+static int g_warp_mode = 0; /* set per solve through prob_t; the vector helpers read it */
 static double dot(int n, const double *a, const double *b) {
+  if (g_warp_mode) {
+    double t[WL];
+    for (int k = 0; k < WL; k++)
+      t[k] = (2 * k + 1 < n) ? pdot(a[2 * k], a[2 * k + 1], b[2 * k], b[2 * k + 1]) : 0.0;
+    return w_sum(t);
+  }
   double s = 0.0;
   for (int i = 0; i < n; i++) s += a[i] * b[i];
   return s;
 }
 static double norm2(int n, const double *a) { return sqrt(dot(n, a, a)); }
 static double norm2sq_diff(int n, const double *a, const double *b) {
-  double s = 0.0;
-  for (int i = 0; i < n; i++) s += (a[i] - b[i]) * (a[i] - b[i]);
-  return s;
+  double d[MAXNU];
+  for (int i = 0; i < n; i++) d[i] = a[i] - b[i];
+  return dot(n, d, d);
 }
 
 /* ---- lbfgs crate: Lbfgs with C-BFGS (Li & Fukushima) safeguard ---- */
@@ -447,18 +822,18 @@ static void lb_apply(lbfgs_t *l, double *q) {
     int k = lb_idx(l, i);
     double a = l->rho[k] * dot(n, l->s[k], q);
     l->alpha[i] = a;
-    for (int t = 0; t < n; t++) q[t] += -a * l->y[k][t];
+    for (int t = 0; t < n; t++) q[t] = fma(-a, l->y[k][t], q[t]);
   }
   for (int t = 0; t < n; t++) q[t] *= l->gamma;
   for (int i = l->active - 1; i >= 0; i--) {
     int k = lb_idx(l, i);
     double beta = l->rho[k] * dot(n, l->y[k], q);
     double cf = l->alpha[i] - beta;
-    for (int t = 0; t < n; t++) q[t] += cf * l->s[k][t];
+    for (int t = 0; t < n; t++) q[t] = fma(cf, l->s[k][t], q[t]);
   }
 }
-/* returns 1 if accepted */
-static int lb_update(lbfgs_t *l, const double *g, const double *state) {
+/* returns 1 if accepted; norm_g = |g| (the caller already has it) */
+static int lb_update(lbfgs_t *l, const double *g, const double *state, double norm_g) {
   const int n = l->n;
   if (l->first_old) {
     l->first_old = 0;
@@ -473,11 +848,12 @@ static int lb_update(lbfgs_t *l, const double *g, const double *state) {
   }
   double ys = dot(n, l->s[last], l->y[last]);
   double ss = dot(n, l->s[last], l->s[last]);
+  double yy = dot(n, l->y[last], l->y[last]);
   l->rho[last] = 1.0 / ys;
   if (ss <= DBL_MIN || (l->sy_eps > 0.0 && ys <= l->sy_eps)) return 0;
   if (l->cbfgs_eps > 0.0 && l->cbfgs_alpha > 0.0) {
     double lhs = ys / ss;
-    double rhs = l->cbfgs_eps * pow(norm2(n, g), l->cbfgs_alpha);
+    double rhs = l->cbfgs_eps * norm_g; /* pow(|g|, cbfgs_alpha) with alpha = 1 */
     if (!(lhs > rhs && isfinite(lhs) && isfinite(rhs))) return 0;
   }
   memcpy(l->old_state, state, n * sizeof(double));
@@ -485,7 +861,7 @@ static int lb_update(lbfgs_t *l, const double *g, const double *state) {
   /* rotate_right(1): the scratch slot becomes slot 0 */
   l->head = (l->head + l->mem) % (l->mem + 1);
   int k0 = lb_idx(l, 0);
-  l->gamma = (1.0 / l->rho[k0]) / dot(n, l->y[k0], l->y[k0]);
+  l->gamma = (1.0 / l->rho[k0]) / yy;
   l->active = (l->mem < l->active + 1) ? l->mem : l->active + 1;
   return 1;
 }
@@ -521,15 +897,12 @@ static void pc_set_akkt(panoc_t *c, double tol) {
 }
 static int pc_exit(const panoc_t *c) {
   if (!(c->norm_fpr < c->tolerance)) return 0;
-  double r = 0.0;
-  for (int i = 0; i < c->n; i++) {
-    double t = c->fpr[i] + c->gamma * (c->grad[i] - c->grad_prev[i]);
-    r += t * t;
-  }
-  return sqrt(r) < c->akkt_tol;
+  double r[MAXNU];
+  for (int i = 0; i < c->n; i++) r[i] = fma(c->gamma, c->grad[i] - c->grad_prev[i], c->fpr[i]);
+  return sqrt(dot(c->n, r, r)) < c->akkt_tol;
 }
 static void pe_gradient_step(panoc_t *c, const double *u) {
-  for (int i = 0; i < c->n; i++) c->gstep[i] = u[i] - c->gamma * c->grad[i];
+  for (int i = 0; i < c->n; i++) c->gstep[i] = fma(-c->gamma, c->grad[i], u[i]);
 }
 static void pe_half_step(panoc_t *c, const ttmpc_config *g) {
   memcpy(c->u_half, c->gstep, c->n * sizeof(double));
@@ -552,9 +925,9 @@ static void pe_init(panoc_t *c, prob_t *pb, double *u) {
                                                          : DELTA_LIPSCHITZ;
       up[i] = u[i] + h[i];
     }
-    double nh = norm2(n, h);
+    double nh = dot(n, h, h);
     f_grad(pb, up, g2);
-    c->L = sqrt(norm2sq_diff(n, g2, c->grad)) / nh;
+    c->L = sqrt(norm2sq_diff(n, g2, c->grad)) / sqrt(nh);
   }
   c->gamma = GAMMA_L_COEFF / fmax(c->L, MIN_L_ESTIMATE);
   c->sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * c->gamma);
@@ -587,13 +960,13 @@ static void pe_update_lipschitz(panoc_t *c, prob_t *pb, const double *u) {
 static int pe_ls_condition(panoc_t *c, prob_t *pb, const double *u) {
   const int n = c->n;
   const double tau = c->tau, one_m = 1.0 - tau;
-  for (int i = 0; i < n; i++) c->u_plus[i] = u[i] - one_m * c->fpr[i] - tau * c->dir[i];
+  for (int i = 0; i < n; i++) c->u_plus[i] = fma(-tau, c->dir[i], fma(-one_m, c->fpr[i], u[i]));
   f_cost(pb, c->u_plus, &c->cost);
   f_grad(pb, c->u_plus, c->grad);
-  for (int i = 0; i < n; i++) c->gstep[i] = c->u_plus[i] - c->gamma * c->grad[i];
+  for (int i = 0; i < n; i++) c->gstep[i] = fma(-c->gamma, c->grad[i], c->u_plus[i]);
   pe_half_step(c, pb->g);
-  c->lhs_ls = c->cost - 0.5 * c->gamma * dot(n, c->grad, c->grad) +
-              0.5 * norm2sq_diff(n, c->u_half, c->gstep) / c->gamma;
+  const double dd = norm2sq_diff(n, c->u_half, c->gstep), g2 = dot(n, c->grad, c->grad);
+  c->lhs_ls = c->cost - 0.5 * c->gamma * g2 + 0.5 * dd / c->gamma;
   return c->lhs_ls > c->rhs_ls;
 }
 /* returns 1 to continue */
@@ -604,7 +977,7 @@ static int pe_step(panoc_t *c, prob_t *pb, double *u) {
   if (pc_exit(c)) return 0;
   pe_update_lipschitz(c, pb, u);
   /* lbfgs_direction */
-  lb_update(&c->lb, c->fpr, u);
+  lb_update(&c->lb, c->fpr, u, c->norm_fpr);
   if (c->iteration > 0) {
     memcpy(c->dir, c->fpr, n * sizeof(double));
     lb_apply(&c->lb, c->dir);
@@ -618,8 +991,8 @@ static int pe_step(panoc_t *c, prob_t *pb, double *u) {
     pe_half_step(c, pb->g);
   } else {
     /* linesearch */
-    double d2 = norm2sq_diff(n, c->gstep, c->u_half);
-    double fbe = c->cost - 0.5 * c->gamma * dot(n, c->grad, c->grad) + 0.5 * d2 / c->gamma;
+    const double dist2 = norm2sq_diff(n, c->gstep, c->u_half), gg = dot(n, c->grad, c->grad);
+    const double fbe = c->cost - 0.5 * c->gamma * gg + 0.5 * dist2 / c->gamma;
     c->rhs_ls = fbe - c->sigma * (c->norm_fpr * c->norm_fpr);
     c->tau = 1.0;
     int nls = 0;
@@ -651,16 +1024,18 @@ static int panoc_solve(panoc_t *c, prob_t *pb, double *u, int max_iter, int *ite
 }
 
 /* ---- ALM / PM outer loop (alm_optimizer.rs) ---- */
-int ttmpc_oracle_solve(const ttmpc_config *g, const double *p, double *u, double *y,
-                       double c0, ttmpc_oracle_status *st) {
+static int solve_mode(const ttmpc_config *g, const double *p, double *u, double *y, double c0,
+                      ttmpc_oracle_status *st, int warp) {
   const int N = g->N_hor, n = 2 * N, n1 = 2 * N, n2 = g->Ndynobs;
   panoc_t *pc = (panoc_t *)calloc(1, sizeof(panoc_t));
-  prob_t pb = {g, p, c0, y, 0, 0};
+  prob_t pb = {g, p, c0, y, 0, 0, warp, NULL};
   double y_plus[MAXNU], w1[MAXNU], w2[MAXDYN];
   double delta_y_norm = 0.0, delta_y_norm_plus = 0.0, f2_norm = 0.0, f2_norm_plus = 0.0;
-  double last_fpr = 0.0;
+  double last_fpr = 0.0, f_final = 0.0;
   int alm_iter = 0, inner_count = 0, num_outer = 0, exit_status = TTMPC_CONVERGED;
   const double SMALL_EPSILON = DBL_EPSILON;
+  g_warp_mode = warp;
+  if (warp) { pb.W = (wstage_t *)malloc(sizeof(wstage_t)); w_stage(g, p, pb.W); }
 
   pc->n = n;
   lb_init(&pc->lb, n, g->lbfgs_memory);
@@ -674,21 +1049,40 @@ int ttmpc_oracle_solve(const ttmpc_config *g, const double *p, double *u, double
     for (int i = 0; i < n1; i++) y[i] = clip(y[i], -1e12, 1e12);
     int it = 0;
     int inner_status = panoc_solve(pc, &pb, u, g->max_inner_iterations, &it);
+    inner_count += it;
     if (inner_status == TTMPC_NOT_FINITE) { exit_status = TTMPC_NOT_FINITE; break; }
     last_fpr = pc->norm_fpr;
-    inner_count += it;
     /* update Lagrange multipliers: y+ = y + c (F1(u) - Proj_C(F1(u) + y/max(c,1))) */
-    ttmpc_oracle_eval(g, u, p, NULL, w1, w2);
+    if (warp) {
+      wout_t e = w_eval(g, p, pb.W, u, 0.0, NULL, NULL, NULL);
+      pb.n_cost++;
+      f2_norm_plus = sqrt(e.f2sq);
+      f_final = e.f;
+      for (int k = 0; k < N; k++) {
+        w1[k] = (u[2 * k] - (k ? u[2 * (k - 1)] : p[6])) / g->ts;
+        w1[N + k] = (u[2 * k + 1] - (k ? u[2 * (k - 1) + 1] : p[7])) / g->ts;
+      }
+    } else {
+      ttmpc_oracle_eval(g, u, p, &f_final, w1, w2);
+      pb.n_cost++;
+      f2_norm_plus = norm2(n2, w2);
+    }
     for (int i = 0; i < n1; i++) {
       double lo = i < N ? g->lin_acc_min : -g->ang_acc_max;
       double hi = i < N ? g->lin_acc_max : g->ang_acc_max;
-      double t = w1[i] + y[i] / fmax(pb.c, 1.0);
-      t = clip(t, lo, hi);
+      double t = clip(w1[i] + y[i] / fmax(pb.c, 1.0), lo, hi);
       y_plus[i] = y[i] + pb.c * (w1[i] - t);
     }
-    /* infeasibilities */
-    f2_norm_plus = norm2(n2, w2);
-    delta_y_norm_plus = sqrt(norm2sq_diff(n1, y_plus, y));
+    if (warp) { /* lane k pairs the k-th linear and angular rows */
+      double t[WL];
+      for (int k = 0; k < WL; k++) {
+        double da = k < N ? y_plus[k] - y[k] : 0.0, dw = k < N ? y_plus[N + k] - y[N + k] : 0.0;
+        t[k] = pdot(da, dw, da, dw);
+      }
+      delta_y_norm_plus = sqrt(w_sum(t));
+    } else {
+      delta_y_norm_plus = sqrt(norm2sq_diff(n1, y_plus, y));
+    }
     /* exit criterion */
     int crit1 = alm_iter > 0 && delta_y_norm_plus <= pb.c * g->delta_tolerance + SMALL_EPSILON;
     int crit2 = f2_norm_plus <= g->delta_tolerance + SMALL_EPSILON;
@@ -715,8 +1109,6 @@ int ttmpc_oracle_solve(const ttmpc_config *g, const double *p, double *u, double
      Solver object keeps exactly this vector between run() calls.             */
 
   if (st) {
-    double f = 0.0;
-    ttmpc_oracle_eval(g, u, p, &f, NULL, NULL);
     st->exit_status = exit_status;
     st->outer_iters = num_outer;
     st->inner_iters = inner_count;
@@ -724,23 +1116,32 @@ int ttmpc_oracle_solve(const ttmpc_config *g, const double *p, double *u, double
     st->delta_y_norm = delta_y_norm_plus;
     st->f2_norm = f2_norm_plus;
     st->penalty = pb.c;
-    st->cost = f;
+    st->cost = f_final;
     st->n_cost_evals = pb.n_cost;
     st->n_grad_evals = pb.n_grad;
   }
+  if (pb.W) free(pb.W);
   free(pc);
   return 0;
 }
 
+int ttmpc_oracle_solve(const ttmpc_config *g, const double *p, double *u, double *y, double c0,
+                       ttmpc_oracle_status *st) {
+  return solve_mode(g, p, u, y, c0, st, 0);
+}
+int ttmpc_oracle_solve_warp(const ttmpc_config *g, const double *p, double *u, double *y,
+                            double c0, ttmpc_oracle_status *st) {
+  return solve_mode(g, p, u, y, c0, st, 1);
+}
+
 typedef struct {
   const ttmpc_config *g;
-  int n, lo, hi, use_u0, use_y0;
+  int n, lo, hi, use_u0, use_y0, warp;
   const double *p, *c0;
   const ttmpc_result *res;
 } job_t;
 
-static void *batch_worker(void *arg) {
-  job_t *jb = (job_t *)arg;
+static void batch_range(job_t *jb) {
   const ttmpc_config *g = jb->g;
   const int N = g->N_hor, nu = 2 * N, np = offsets(g).np;
   for (int i = jb->lo; i < jb->hi; i++) {
@@ -751,7 +1152,7 @@ static void *batch_worker(void *arg) {
       y[t] = (jb->use_y0 && jb->res->y) ? jb->res->y[(size_t)i * nu + t] : 0.0;
     }
     double c0 = jb->c0 ? jb->c0[i] : g->initial_penalty;
-    ttmpc_oracle_solve(g, jb->p + (size_t)i * np, u, y, c0, &st);
+    solve_mode(g, jb->p + (size_t)i * np, u, y, c0, &st, jb->warp);
     const ttmpc_result *r = jb->res;
     memcpy(r->u + (size_t)i * nu, u, nu * sizeof(double));
     if (r->y) memcpy(r->y + (size_t)i * nu, y, nu * sizeof(double));
@@ -763,29 +1164,47 @@ static void *batch_worker(void *arg) {
     if (r->f1_infeas) r->f1_infeas[i] = st.delta_y_norm / st.penalty;
     if (r->f2_norm) r->f2_norm[i] = st.f2_norm;
     if (r->penalty) r->penalty[i] = st.penalty;
-    if (r->pred_states)
-      ttmpc_oracle_rollout(g, u, jb->p + (size_t)i * np, r->pred_states + (size_t)i * N * 3);
+    if (r->pred_states) {
+      if (jb->warp) {
+        wstage_t *W = (wstage_t *)malloc(sizeof(wstage_t));
+        w_stage(g, jb->p + (size_t)i * np, W);
+        w_eval(g, jb->p + (size_t)i * np, W, u, 0.0, NULL, NULL, r->pred_states + (size_t)i * N * 3);
+        free(W);
+      } else {
+        ttmpc_oracle_rollout(g, u, jb->p + (size_t)i * np, r->pred_states + (size_t)i * N * 3);
+      }
+    }
     if (r->evals) { r->evals[2 * i] = st.n_cost_evals; r->evals[2 * i + 1] = st.n_grad_evals; }
   }
-  return NULL;
 }
 
-int ttmpc_oracle_solve_batch(const ttmpc_config *g, int n, const double *p, int use_u0,
-                             int use_y0, const double *c0, const ttmpc_result *res,
-                             int threads) {
+/* The vector helpers read the process-wide g_warp_mode, so a batch runs in ONE
+ * ordering; worker PROCESSES (fork) give the parallelism, threads would share
+ * the flag safely too because every job of a batch uses the same mode.        */
+static void *batch_worker(void *arg) { batch_range((job_t *)arg); return NULL; }
+
+int ttmpc_oracle_solve_batch_mode(const ttmpc_config *g, int n, const double *p, int use_u0,
+                                  int use_y0, const double *c0, const ttmpc_result *res,
+                                  int threads, int warp) {
   if (threads < 1) threads = 1;
   if (threads > 256) threads = 256;
   if (threads > n) threads = n > 0 ? n : 1;
   pthread_t th[256];
   job_t jobs[256];
   int per = (n + threads - 1) / threads;
+  g_warp_mode = warp;
   for (int t = 0; t < threads; t++) {
-    job_t jb = {g, n, t * per, (t + 1) * per < n ? (t + 1) * per : n, use_u0, use_y0, p, c0, res};
+    int lo = t * per, hi = (t + 1) * per < n ? (t + 1) * per : n;
+    job_t jb = {g, n, lo, hi > lo ? hi : lo, use_u0, use_y0, warp, p, c0, res};
     jobs[t] = jb;
-    if (threads == 1) batch_worker(&jobs[t]);
+    if (threads == 1) batch_range(&jobs[t]);
     else pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
   }
   if (threads > 1)
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
   return 0;
+}
+int ttmpc_oracle_solve_batch(const ttmpc_config *g, int n, const double *p, int use_u0,
+                             int use_y0, const double *c0, const ttmpc_result *res, int threads) {
+  return ttmpc_oracle_solve_batch_mode(g, n, p, use_u0, use_y0, c0, res, threads, 0);
 }

@@ -52,6 +52,17 @@ void ttmpc_oracle_psi_grad(const ttmpc_config *cfg, const double *u, const doubl
  * y: in = initial Lagrange multipliers, out = final (len 2N).          */
 int ttmpc_oracle_solve(const ttmpc_config *cfg, const double *p, double *u,
                        double *y, double c0, ttmpc_oracle_status *st);
+/* Same solve with the arithmetic ORDER of the CUDA kernel (32-lane scans and
+ * butterfly sums, explicit fma, tt_sincos): reproduces the GPU bit for bit.   */
+int ttmpc_oracle_solve_warp(const ttmpc_config *cfg, const double *p, double *u,
+                            double *y, double c0, ttmpc_oracle_status *st);
+void ttmpc_oracle_eval_warp(const ttmpc_config *cfg, const double *u, const double *p,
+                            double c, const double *y, double *f, double *F2,
+                            double *psi, double *grad);
+void ttmpc_oracle_sincos(double x, double *s, double *c);
+int ttmpc_oracle_solve_batch_mode(const ttmpc_config *cfg, int n, const double *p,
+                                  int use_u0, int use_y0, const double *c0,
+                                  const ttmpc_result *res, int threads, int warp);
 /* Batched convenience (sequential loop, or `threads` pthreads).
  * Same per-scene arrays as ttmpc_result (host pointers).               */
 int ttmpc_oracle_solve_batch(const ttmpc_config *cfg, int n, const double *p,

@@ -48,6 +48,9 @@ def load():
         lib.ttmpc_oracle_solve.argtypes = [CFG, VP, VP, VP, D, C.POINTER(OracleStatus)]
         lib.ttmpc_oracle_solve_batch.argtypes = [CFG, I, VP, I, I, VP, C.POINTER(TtmpcResult), I]
         lib.ttmpc_oracle_rollout.argtypes = [CFG, VP, VP, VP]
+        lib.ttmpc_oracle_solve_batch_mode.argtypes = [CFG, I, VP, I, I, VP, C.POINTER(TtmpcResult), I, I]
+        lib.ttmpc_oracle_eval_warp.argtypes = [CFG, VP, VP, D, VP, VP, VP, VP, VP]
+        lib.ttmpc_oracle_sincos.argtypes = [D, C.POINTER(D), C.POINTER(D)]
         lib.ttdqn_oracle_observe_act.argtypes = [C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet), I] + [VP] * 12
         _lib = lib
     return _lib
@@ -82,8 +85,26 @@ def psi_grad(cfg, u, p, c, y=None):
     return g
 
 
-def solve_batch(cfg, p, u0=None, y0=None, c0=None, threads=1):
-    """Same outputs as BatchSolver.run (dict of numpy arrays)."""
+def eval_warp(cfg, u, p, c=0.0, y=None):
+    """f, F2, psi, grad psi with the GPU's operation order (bit-exact mirror)."""
+    lib = load()
+    u = np.ascontiguousarray(u, np.float64); p = np.ascontiguousarray(p, np.float64)
+    y = None if y is None else np.ascontiguousarray(y, np.float64)
+    f = np.zeros(1); ps = np.zeros(1); F2 = np.zeros(max(cfg.Ndynobs, 1)); g = np.zeros(2 * cfg.N_hor)
+    lib.ttmpc_oracle_eval_warp(C.byref(cfg), _p(u), _p(p), float(c), _p(y), _p(f), _p(F2), _p(ps), _p(g))
+    return float(f[0]), F2[:cfg.Ndynobs], float(ps[0]), g
+
+
+def sincos(x):
+    lib = load()
+    s = C.c_double(); c = C.c_double()
+    lib.ttmpc_oracle_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def solve_batch(cfg, p, u0=None, y0=None, c0=None, threads=1, warp=False):
+    """Same outputs as BatchSolver.run (dict of numpy arrays).
+    warp=True uses the GPU's operation order (bit-exact mirror of the kernel)."""
     lib = load()
     p = np.ascontiguousarray(p, np.float64)
     n, N = p.shape[0], cfg.N_hor
@@ -97,8 +118,8 @@ def solve_batch(cfg, p, u0=None, y0=None, c0=None, threads=1):
                       outer_iters=_p(out["outer"]), inner_iters=_p(out["inner"]), last_fpr=_p(out["fpr"]),
                       f1_infeas=_p(out["f1"]), f2_norm=_p(out["f2"]), penalty=_p(out["pen"]), y=_p(y),
                       pred_states=_p(out["pred"]), evals=_p(out["evals"]))
-    lib.ttmpc_oracle_solve_batch(C.byref(cfg), n, _p(p), int(u0 is not None), int(y0 is not None),
-                                 _p(c0a), C.byref(res), int(threads))
+    lib.ttmpc_oracle_solve_batch_mode(C.byref(cfg), n, _p(p), int(u0 is not None), int(y0 is not None),
+                                      _p(c0a), C.byref(res), int(threads), int(warp))
     out["u"] = u; out["y"] = y
     return out
 

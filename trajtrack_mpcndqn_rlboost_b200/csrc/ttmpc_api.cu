@@ -82,7 +82,7 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   g->np = g->off_qdyn + N;
   g->warps_per_block = 4;
   g->smem_per_warp = smem_bytes_per_warp(N, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
-  g->ts = c->ts; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;
+  g->ts = c->ts; g->h6 = c->ts / 6.0; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;
   g->vmin = c->lin_vel_min; g->vmax = c->lin_vel_max; g->wmax = c->ang_vel_max;
   g->amin = c->lin_acc_min; g->amax = c->lin_acc_max; g->awmax = c->ang_acc_max;
   g->tol = c->tolerance; g->init_tol = c->initial_tolerance; g->delta_tol = c->delta_tolerance;

@@ -6,6 +6,13 @@
 // adjoint become warp prefix / suffix scans; every inner product is a butterfly
 // all-reduce, so all solver control flow is warp-uniform.
 //
+// ARITHMETIC CONTRACT.  This file is compiled with -fmad=false: the only fused
+// multiply-adds are the explicit fma() calls below, trigonometry is tt_sincos
+// (Cody-Waite + fdlibm kernels, +,*,fma only), divisions and square roots are
+// IEEE.  The CPU oracle (oracle/ttmpc_oracle.c, WARP ordering) performs the same
+// operations in the same order, so a GPU solve is reproducible bit for bit on
+// the host.  Change an expression here and the oracle's mirror must change too.
+//
 // Reference for the maths:
 //   cost / constraints : /root/reference/src/mpc_traj_tracker/mpc/mpc_generator.py:155-283
 //   dynamics           : /root/reference/src/pkg_motion_model/motion_model.py:153-176
@@ -23,17 +30,48 @@ namespace ttmpc {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_MEM = 16;
 constexpr int MAX_EDGE = 8;
-constexpr int DYN_FIELDS = 10;  // per (obstacle, step): see build_dyn_table
+constexpr int DYN_FIELDS = 10;  // per (obstacle, step): see stage_scene
 
 struct DevCfg {
   int N, Nother, Nstc, ne, nstcobs, Ndyn, mem, max_inner, max_outer;
   int off_s, off_q, off_r, off_vref, off_c, off_os, off_od, off_qdyn, np;
   int smem_per_warp;  // bytes
   int warps_per_block;
-  double ts, veh_d2, margin;
+  double ts, h6, veh_d2, margin;
   double vmin, vmax, wmax, amin, amax, awmax;
   double tol, init_tol, delta_tol, c0, pen_factor, tol_factor, suff_dec;
 };
+
+// ---------------------------------------------------------------- sincos
+// Cody-Waite reduction by pi/2 (three fma steps, exact products) and the fdlibm
+// __kernel_sin / __kernel_cos minimax polynomials.  <= 1 ulp on |x| < 1e9.
+__host__ __device__ __forceinline__ void tt_sincos(double x, double *s, double *c) {
+  if (!(fabs(x) < 1.0e9)) { *s = x * 0.0 + NAN; *c = *s; return; }
+  const double kd = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-kd, 1.5707963267948966e+00, x);
+  r = fma(-kd, 6.123233995736766e-17, r);
+  r = fma(-kd, -1.4973849048591698e-33, r);
+  const int q = (int)((long long)kd & 3);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  switch (q) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+  }
+}
 
 // ---------------------------------------------------------------- warp utils
 __device__ __forceinline__ double wsum(double v) {
@@ -71,6 +109,10 @@ __device__ __forceinline__ double wsuffix(double v, int lane) {
 __device__ __forceinline__ double clipd(double z, double lo, double hi) {
   return fmin(fmax(z, lo), hi);
 }
+// per-lane share of an inner product of two lane-distributed vectors
+__device__ __forceinline__ double pdot(double a0, double a1, double b0, double b1) {
+  return fma(a1, b1, a0 * b0);
+}
 
 // ---------------------------------------------------------------- per-warp state
 // Everything a warp needs that is uniform across lanes lives in shared memory
@@ -86,7 +128,7 @@ struct WarpCtx {
 struct WarpSmem {
   WarpCtx *ctx;
   double *seg;   // [5][N]: s1x s1y sx sy inv_den
-  double *os;    // [Nstc*nstcobs] raw static half-spaces
+  double *os;    // [Nstc*nstcobs] per obstacle: b[ne], -a0[ne], -a1[ne]
   double *D;     // [Ndyn] per-obstacle hard sums of the last evaluation
   double2 *lbs;  // [(mem+1)][N]
   double2 *lby;  // [(mem+1)][N]
@@ -101,8 +143,8 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nstc, int nstcobs,
   b += sizeof(double) * Nstc * nstcobs;
   b += sizeof(double) * ((Ndyn + 1) / 2 * 2);
   b += sizeof(double2) * (size_t)(mem + 1) * N * 2;
-  b += sizeof(double) * (mem + 2) / 2 * 2;
-  b += sizeof(double) * (mem + 1) / 2 * 2;
+  b += sizeof(double) * ((mem + 2) / 2 * 2);
+  b += sizeof(double) * ((mem + 1) / 2 * 2);
   return (int)((b + 15) / 16 * 16);
 }
 
@@ -125,9 +167,6 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
 // (mpc_generator.py:225-237): the sincos and the four divisions leave the hot loop.
 //   0 cx  1 cy  2 R2 (rejection radius^2)  3 cos  4 sin
 //   5 1/(rx+1e-6)^2  6 1/(ry+1e-6)^2  7 1/(rx+m+1e-6)^2  8 1/(ry+m+1e-6)^2  9 alpha*qdyn[k]
-__device__ __forceinline__ size_t dyn_table_doubles(const DevCfg &g) {
-  return (size_t)DYN_FIELDS * g.Ndyn * g.N;
-}
 __device__ __forceinline__ double &dynf(double *t, const DevCfg &g, int f, int j, int k) {
   return t[((size_t)f * g.Ndyn + j) * g.N + k];
 }
@@ -151,13 +190,17 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     int j2 = (j + 1 < g.N) ? j + 1 : g.N - 1;
     double s1x = r[3 * j], s1y = r[3 * j + 1];
     double sx = r[3 * j2] - s1x, sy = r[3 * j2 + 1] - s1y;
-    double den = sx * sx + sy * sy + 1e-16;
+    double den = fma(sy, sy, sx * sx) + 1e-16;
     sm.seg[0 * g.N + j] = s1x; sm.seg[1 * g.N + j] = s1y;
     sm.seg[2 * g.N + j] = sx;  sm.seg[3 * g.N + j] = sy;
     sm.seg[4 * g.N + j] = 1.0 / den;
   }
+  // static half-spaces: keep b, store -a0 and -a1 (res = b + (-a0) x + (-a1) y)
   const double *os = p + g.off_os;
-  for (int i = lane; i < g.Nstc * g.nstcobs; i += 32) sm.os[i] = os[i];
+  for (int i = lane; i < g.Nstc * g.nstcobs; i += 32) {
+    const int e = i % g.nstcobs;
+    sm.os[i] = (e < g.ne) ? os[i] : -os[i];
+  }
   // dynamic obstacle table
   const double *od = p + g.off_od, *qdyn = p + g.off_qdyn;
   const int npair = g.Ndyn * g.N;
@@ -166,7 +209,7 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     const double *e = od + (size_t)t * 6;  // obstacle-major, then step: contiguous records
     double cx = e[0], cy = e[1], rx = e[2], ry = e[3], ang = e[4], alpha = e[5];
     double sa, ca;
-    sincos(ang, &sa, &ca);
+    tt_sincos(ang, &sa, &ca);
     double Rx = rx + 1e-6, Ry = ry + 1e-6;
     double Rxm = rx + g.margin + 1e-6, Rym = ry + g.margin + 1e-6;
     double rmax = fmax(fmax(fabs(Rx), fabs(Ry)), fmax(fabs(Rxm), fabs(Rym)));
@@ -208,22 +251,21 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   const bool act = lane < N;
   const double ts = g.ts;
 
-  // ---- rollout (motion_model.py:153-176): theta and position as prefix sums
+  // ---- rollout (motion_model.py:153-176; RK4 of the unicycle = Simpson in theta):
+  //      theta and position are prefix sums over the lanes
   const double tw = ts * w;
-  const double dth = (1.0 / 6.0) * (tw + 2 * tw + 2 * tw + tw);
-  const double th_in = wscan(dth, lane);
+  const double th_in = wscan(tw, lane);
   double th_ex = __shfl_up_sync(FULL, th_in, 1);
   if (lane == 0) th_ex = 0.0;
   const double tha = cx->th0 + th_ex;
-  const double thb = tha + 0.5 * tw, thc = tha + tw;
+  const double thb = fma(0.5, tw, tha), thc = tha + tw;
   double sa, ca, sb, cb, sc, cc;
-  sincos(tha, &sa, &ca);
-  sincos(thb, &sb, &cb);
-  sincos(thc, &sc, &cc);
-  const double k1x = ts * (v * ca), k2x = ts * (v * cb), k4x = ts * (v * cc);
-  const double k1y = ts * (v * sa), k2y = ts * (v * sb), k4y = ts * (v * sc);
-  const double dx = (1.0 / 6.0) * (k1x + 2 * k2x + 2 * k2x + k4x);
-  const double dy = (1.0 / 6.0) * (k1y + 2 * k2y + 2 * k2y + k4y);
+  tt_sincos(tha, &sa, &ca);
+  tt_sincos(thb, &sb, &cb);
+  tt_sincos(thc, &sc, &cc);
+  const double Cs = fma(4.0, cb, ca) + cc, Ss = fma(4.0, sb, sa) + sc;
+  const double hv = g.h6 * v;
+  const double dx = hv * Cs, dy = hv * Ss;
   const double X = cx->x0 + wscan(dx, lane);
   const double Y = cx->y0 + wscan(dy, lane);
   const double TH = cx->th0 + th_in;
@@ -233,41 +275,45 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   double gx = 0.0, gy = 0.0; // d psi / d position_{k+1}
   double S_loc = 0.0, gSx = 0.0, gSy = 0.0;
 
-  // ---- reference-path deviation (l.124-139, 202)
+  // ---- reference-path deviation (l.124-139, 202): min over the remaining segments
   {
     double dmin = 0.0; int jmin = lane;
     for (int j = 0; j < N; j++) {
       const double s1x = sm.seg[j], s1y = sm.seg[N + j], sx = sm.seg[2 * N + j],
                    sy = sm.seg[3 * N + j], inv = sm.seg[4 * N + j];
       if (j >= lane) {
-        double t_hat = ((X - s1x) * sx + (Y - s1y) * sy) * inv;
-        double t = fmin(fmax(t_hat, 0.0), 1.0);
-        double qx = s1x + t * sx - X, qy = s1y + t * sy - Y;
-        double d2 = qx * qx + qy * qy;
+        const double px = X - s1x, py = Y - s1y;
+        const double t_hat = fma(py, sy, px * sx) * inv;
+        const double t = fmin(fmax(t_hat, 0.0), 1.0);
+        const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
+        const double d2 = fma(qy, qy, qx * qx);
         if (j == lane || !(dmin <= d2)) { dmin = d2; jmin = j; }
       }
     }
     if (act) {
-      cost += dmin * cx->qrpd;
+      cost = dmin * cx->qrpd;
       if (GRAD) {
         const int j = jmin;
         const double s1x = sm.seg[j], s1y = sm.seg[N + j], sx = sm.seg[2 * N + j],
                      sy = sm.seg[3 * N + j], inv = sm.seg[4 * N + j];
-        double t_hat = ((X - s1x) * sx + (Y - s1y) * sy) * inv;
-        double t = fmin(fmax(t_hat, 0.0), 1.0);
-        double qx = s1x + t * sx - X, qy = s1y + t * sy - Y;
-        double pass = (t_hat >= 0.0 && t_hat <= 1.0) ? 1.0 : 0.0;
-        double cs = (qx * sx + qy * sy) * pass * inv;
-        gx += cx->qrpd * (2 * (cs * sx - qx));
-        gy += cx->qrpd * (2 * (cs * sy - qy));
+        const double px = X - s1x, py = Y - s1y;
+        const double t_hat = fma(py, sy, px * sx) * inv;
+        const double t = fmin(fmax(t_hat, 0.0), 1.0);
+        const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
+        const double pass = (t_hat >= 0.0 && t_hat <= 1.0) ? 1.0 : 0.0;
+        const double cs = fma(qy, sy, qx * sx) * pass * inv;
+        gx = cx->qrpd * (2.0 * fma(cs, sx, -qx));
+        gy = cx->qrpd * (2.0 * fma(cs, sy, -qy));
       }
     }
   }
   // ---- speed reference + control action (l.203-204)
+  double vr = 0.0;
   if (act) {
-    const double vr = cx->p[g.off_vref + lane];
-    cost += cx->qvel * ((v - vr) * (v - vr));
-    cost += cx->rv * (v * v) + cx->rw * (w * w);
+    vr = cx->p[g.off_vref + lane];
+    const double dv_ = v - vr;
+    cost += cx->qvel * (dv_ * dv_);
+    cost += fma(cx->rw, w * w, cx->rv * (v * v));
   }
   // ---- fleet collision (l.207-211)
   if (act) {
@@ -276,47 +322,14 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     for (int j = 0; j < g.Nother; j++) {
       const double ox = cp[(size_t)j * 3 * N], oy = cp[(size_t)j * 3 * N + 1];
       const double ex = X - ox, ey = Y - oy;
-      const double e = g.veh_d2 - (ex * ex + ey * ey);
+      const double e = g.veh_d2 - fma(ey, ey, ex * ex);
       if (e > 0.0) {
         acc += e;
-        if (GRAD) { fx += -2 * ex; fy += -2 * ey; }
+        if (GRAD) { fx = fma(-2.0, ex, fx); fy = fma(-2.0, ey, fy); }
       }
     }
     cost += 1000.0 * acc;
-    if (GRAD) { gx += 1000.0 * fx; gy += 1000.0 * fy; }
-  }
-  // ---- static obstacles (l.214-220): hard penalty only
-  if (act) {
-    const int ne = g.ne;
-    for (int i = 0; i < g.Nstc; i++) {
-      const double *b = sm.os + i * g.nstcobs, *a0 = b + ne, *a1 = b + 2 * ne;
-      double m[MAX_EDGE];
-      double inside = 1.0;
-#pragma unroll
-      for (int e = 0; e < MAX_EDGE; e++) {
-        if (e < ne) {
-          double res = a0[e] * (-X) + a1[e] * (-Y) + b[e];
-          m[e] = fmax(0.0, res);
-          inside *= m[e] * m[e];
-        }
-      }
-      if (inside > 0.0) {
-        S_loc += inside;
-        if (GRAD) {
-#pragma unroll
-          for (int e = 0; e < MAX_EDGE; e++) {
-            if (e < ne) {
-              double rest = 1.0;
-#pragma unroll
-              for (int e2 = 0; e2 < MAX_EDGE; e2++)
-                if (e2 < ne && e2 != e) rest *= m[e2] * m[e2];
-              gSx += rest * 2 * m[e] * (-a0[e]);
-              gSy += rest * 2 * m[e] * (-a1[e]);
-            }
-          }
-        }
-      }
-    }
+    if (GRAD) { gx = fma(1000.0, fx, gx); gy = fma(1000.0, fy, gy); }
   }
   // ---- dynamic obstacles (l.225-237): hard penalty D_j and soft cost
   unsigned hard_mask_lo = 0, hard_mask_hi = 0;  // obstacles with a positive hard term
@@ -330,27 +343,28 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       if (act) {
         ex = X - T[((size_t)0 * g.Ndyn + j) * N + lane];
         ey = Y - T[((size_t)1 * g.Ndyn + j) * N + lane];
-        pass = (ex * ex + ey * ey) < T[((size_t)2 * g.Ndyn + j) * N + lane];
+        pass = fma(ey, ey, ex * ex) < T[((size_t)2 * g.Ndyn + j) * N + lane];
       }
       double in1 = 0.0;
       if (pass) {
         bodies++;
         const double ca_ = T[((size_t)3 * g.Ndyn + j) * N + lane];
         const double sa_ = T[((size_t)4 * g.Ndyn + j) * N + lane];
-        const double A = ex * ca_ + ey * sa_, B = ex * sa_ - ey * ca_;
+        const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
         const double A2 = A * A, B2 = B * B;
-        in1 = 1 - A2 * T[((size_t)5 * g.Ndyn + j) * N + lane] -
-              B2 * T[((size_t)6 * g.Ndyn + j) * N + lane];
+        in1 = fma(-B2, T[((size_t)6 * g.Ndyn + j) * N + lane],
+                  fma(-A2, T[((size_t)5 * g.Ndyn + j) * N + lane], 1.0));
         const double iRxm = T[((size_t)7 * g.Ndyn + j) * N + lane];
         const double iRym = T[((size_t)8 * g.Ndyn + j) * N + lane];
-        const double in2 = 1 - A2 * iRxm - B2 * iRym;
+        const double in2 = fma(-B2, iRym, fma(-A2, iRxm, 1.0));
         if (in2 > 0.0) {
           const double ws = T[((size_t)9 * g.Ndyn + j) * N + lane];
-          soft += (in2 * in2) * ws;
+          soft = fma(in2 * in2, ws, soft);
           if (GRAD) {
-            const double wg = ws * 2 * in2;
-            gx += wg * (-2 * A * ca_ * iRxm - 2 * B * sa_ * iRym);
-            gy += wg * (-2 * A * sa_ * iRxm + 2 * B * ca_ * iRym);
+            const double wg = ws * (2.0 * in2);
+            const double tA = A * iRxm, tB = B * iRym;
+            gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
+            gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);
           }
         }
       }
@@ -370,12 +384,47 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   // ---- terminal cost (l.242)
   double gt = 0.0;
   if (lane == N - 1) {
-    cost += cx->qN * ((X - cx->xg) * (X - cx->xg) + (Y - cx->yg) * (Y - cx->yg)) +
-            cx->qthetaN * ((TH - cx->thg) * (TH - cx->thg));
+    const double dxg = X - cx->xg, dyg = Y - cx->yg, dtg = TH - cx->thg;
+    cost += fma(cx->qthetaN, dtg * dtg, cx->qN * fma(dyg, dyg, dxg * dxg));
     if (GRAD) {
-      gx += 2 * cx->qN * (X - cx->xg);
-      gy += 2 * cx->qN * (Y - cx->yg);
-      gt = 2 * cx->qthetaN * (TH - cx->thg);
+      gx = fma(2.0 * cx->qN, dxg, gx);
+      gy = fma(2.0 * cx->qN, dyg, gy);
+      gt = 2.0 * cx->qthetaN * dtg;
+    }
+  }
+  // ---- static obstacles (l.214-220): hard penalty only
+  if (act) {
+    const int ne = g.ne;
+    for (int i = 0; i < g.Nstc; i++) {
+      const double *b = sm.os + i * g.nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
+      double m[MAX_EDGE], sq[MAX_EDGE];
+      double inside = 1.0;
+#pragma unroll
+      for (int e = 0; e < MAX_EDGE; e++) {
+        if (e < ne) {
+          const double res = fma(na1[e], Y, fma(na0[e], X, b[e]));
+          m[e] = fmax(0.0, res);
+          sq[e] = m[e] * m[e];
+          inside *= sq[e];
+        }
+      }
+      if (inside > 0.0) {
+        S_loc += inside;
+        if (GRAD) {
+#pragma unroll
+          for (int e = 0; e < MAX_EDGE; e++) {
+            if (e < ne) {
+              double rest = 1.0;
+#pragma unroll
+              for (int e2 = 0; e2 < MAX_EDGE; e2++)
+                if (e2 < ne && e2 != e) rest *= sq[e2];
+              const double coef = rest * (2.0 * m[e]);
+              gSx = fma(coef, na0[e], gSx);
+              gSy = fma(coef, na1[e], gSy);
+            }
+          }
+        }
+      }
     }
   }
   // ---- accelerations: cost (l.250-264) and the ALM set C = acc bounds
@@ -384,13 +433,13 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   double aa = 0.0, aw = 0.0, ea = 0.0, ew = 0.0, alm = 0.0;
   if (act) {
     aa = (v - vp) / ts; aw = (w - wp) / ts;
-    cost += (aa * aa) * cx->acc_pen + (aw * aw) * cx->wacc_pen;
+    cost += fma(aw * aw, cx->wacc_pen, (aa * aa) * cx->acc_pen);
     const double cm = fmax(c, 1.0);
     double z = aa + ya / cm;
     ea = z - clipd(z, g.amin, g.amax);
     z = aw + yw / cm;
     ew = z - clipd(z, -g.awmax, g.awmax);
-    alm = ea * ea + ew * ew;
+    alm = fma(ew, ew, ea * ea);
   }
   // ---- reductions: f, ALM distance, static sum
   double f = cost, d2 = alm, S = S_loc;
@@ -399,7 +448,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   double f2sq = 0.0, sumF2 = 0.0;
   for (int j = 0; j < g.Ndyn; j++) {
     const double F2j = S + sm.D[j];
-    f2sq += F2j * F2j;
+    f2sq = fma(F2j, F2j, f2sq);
     sumF2 += F2j;
   }
   EvalOut out;
@@ -409,8 +458,9 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   if (GRAD) {
     // hard-penalty gradient: c * sum_j F2_j * (grad S + grad D_j)
     if (c != 0.0) {
-      gx += c * sumF2 * gSx;
-      gy += c * sumF2 * gSy;
+      const double cs_ = c * sumF2;
+      gx = fma(cs_, gSx, gx);
+      gy = fma(cs_, gSy, gy);
       unsigned mlo = hard_mask_lo, mhi = hard_mask_hi;
       const double *T = cx->dyn;
       while (mlo | mhi) {
@@ -420,35 +470,35 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
         if (act) {
           const double ex = X - T[((size_t)0 * g.Ndyn + j) * N + lane];
           const double ey = Y - T[((size_t)1 * g.Ndyn + j) * N + lane];
-          const double ca_ = T[((size_t)3 * g.Ndyn + j) * N + lane];
-          const double sa_ = T[((size_t)4 * g.Ndyn + j) * N + lane];
-          const double iRx = T[((size_t)5 * g.Ndyn + j) * N + lane];
-          const double iRy = T[((size_t)6 * g.Ndyn + j) * N + lane];
-          const double A = ex * ca_ + ey * sa_, B = ex * sa_ - ey * ca_;
-          const double in1 = 1 - (A * A) * iRx - (B * B) * iRy;
-          if (in1 > 0.0 && (ex * ex + ey * ey) < T[((size_t)2 * g.Ndyn + j) * N + lane]) {
-            const double wg = c * (S + sm.D[j]);
-            gx += wg * (-2 * A * ca_ * iRx - 2 * B * sa_ * iRy);
-            gy += wg * (-2 * A * sa_ * iRx + 2 * B * ca_ * iRy);
+          if (fma(ey, ey, ex * ex) < T[((size_t)2 * g.Ndyn + j) * N + lane]) {
+            const double ca_ = T[((size_t)3 * g.Ndyn + j) * N + lane];
+            const double sa_ = T[((size_t)4 * g.Ndyn + j) * N + lane];
+            const double iRx = T[((size_t)5 * g.Ndyn + j) * N + lane];
+            const double iRy = T[((size_t)6 * g.Ndyn + j) * N + lane];
+            const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
+            const double in1 = fma(-(B * B), iRy, fma(-(A * A), iRx, 1.0));
+            if (in1 > 0.0) {
+              const double wg = c * (S + sm.D[j]);
+              const double tA = A * iRx, tB = B * iRy;
+              gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
+              gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);
+            }
           }
         }
       }
     }
-    // adjoint of the rollout: suffix scans
-    const double h6 = ts / 6.0;
-    const double Cs = ca + 4 * cb + cc, Ss = sa + 4 * sb + sc;
-    const double dxdv = h6 * Cs, dydv = h6 * Ss;
-    const double dxdth = -h6 * v * Ss, dydth = h6 * v * Cs;
-    const double dxdw = -h6 * v * ts * (2 * sb + sc), dydw = h6 * v * ts * (2 * cb + cc);
+    // adjoint of the rollout: suffix scans (d pos_{k+1}/d theta_k = (-dy, dx))
+    const double dxdv = g.h6 * Cs, dydv = g.h6 * Ss;
+    const double hvt = hv * ts;
+    const double dxdw = -(hvt * fma(2.0, sb, sc)), dydw = hvt * fma(2.0, cb, cc);
     const double lx = wsuffix(gx, lane), ly = wsuffix(gy, lane);
-    const double m = lx * dxdth + ly * dydth;
+    const double m = fma(ly, dx, -(lx * dy));
     const double lt = wsuffix(gt + m, lane) - m;
     // direct control terms
     const double aa_n = __shfl_down_sync(FULL, aa, 1), aw_n = __shfl_down_sync(FULL, aw, 1);
     const double ea_n = __shfl_down_sync(FULL, ea, 1), ew_n = __shfl_down_sync(FULL, ew, 1);
     if (act) {
       const bool last = lane == N - 1;
-      const double vr = cx->p[g.off_vref + lane];
       double dv = 2 * cx->qvel * (v - vr) + 2 * cx->rv * v;
       double dw = 2 * cx->rw * w;
       dv += 2 * cx->acc_pen * (aa - (last ? 0.0 : aa_n)) / ts + c * (ea - (last ? 0.0 : ea_n)) / ts;

@@ -66,7 +66,7 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
   }
   const double sv0 = z.u0 - z.os0, sv1 = z.u1 - z.os1;
   const double yv0 = z.f0 - z.og0, yv1 = z.f1 - z.og1;
-  double ys = sv0 * yv0 + sv1 * yv1, ss = sv0 * sv0 + sv1 * sv1, yy = yv0 * yv0 + yv1 * yv1;
+  double ys = pdot(sv0, sv1, yv0, yv1), ss = pdot(sv0, sv1, sv0, sv1), yy = pdot(yv0, yv1, yv0, yv1);
   wsum3(ys, ss, yy);
   const double rho = 1.0 / ys;
   if (ss <= 2.2250738585072014e-308 || ys <= SY_EPSILON) return;
@@ -100,9 +100,9 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
     const int k = lb_slot(g, U, i);
     const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
     const double2 y = act ? sm.lby[k * N + lane] : make_double2(0.0, 0.0);
-    const double a = sm.rho[k] * wsum(s.x * q0 + s.y * q1);
+    const double a = sm.rho[k] * wsum(pdot(s.x, s.y, q0, q1));
     if (lane == 0) sm.alpha[i] = a;
-    q0 += -a * y.x; q1 += -a * y.y;
+    q0 = fma(-a, y.x, q0); q1 = fma(-a, y.y, q1);
   }
   __syncwarp();
   q0 *= U.lb_gamma; q1 *= U.lb_gamma;
@@ -110,9 +110,9 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
     const int k = lb_slot(g, U, i);
     const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
     const double2 y = act ? sm.lby[k * N + lane] : make_double2(0.0, 0.0);
-    const double beta = sm.rho[k] * wsum(y.x * q0 + y.y * q1);
+    const double beta = sm.rho[k] * wsum(pdot(y.x, y.y, q0, q1));
     const double cf = sm.alpha[i] - beta;
-    q0 += cf * s.x; q1 += cf * s.y;
+    q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
   }
   z.d0 = q0; z.d1 = q1;
 }
@@ -140,11 +140,11 @@ __device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm,
 
 __device__ __forceinline__ void compute_fpr(Lane &z, Uni &U) {
   z.f0 = z.u0 - z.h0; z.f1 = z.u1 - z.h1;
-  U.norm_fpr = sqrt(wsum(z.f0 * z.f0 + z.f1 * z.f1));
+  U.norm_fpr = sqrt(wsum(pdot(z.f0, z.f1, z.f0, z.f1)));
 }
 __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z, const Uni &U,
                                                        double a0, double a1) {
-  z.s0 = a0 - U.gamma * z.g0; z.s1 = a1 - U.gamma * z.g1;
+  z.s0 = fma(-U.gamma, z.g0, a0); z.s1 = fma(-U.gamma, z.g1, a1);
   project(g, z.s0, z.s1, z.h0, z.h1);
 }
 
@@ -154,15 +154,15 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
   compute_fpr(z, U);
   if (U.norm_fpr < tolerance) {
-    const double r0 = z.f0 + U.gamma * (z.g0 - z.gp0), r1 = z.f1 + U.gamma * (z.g1 - z.gp1);
-    if (sqrt(wsum(r0 * r0 + r1 * r1)) < U.akkt_tol) return false;
+    const double r0 = fma(U.gamma, z.g0 - z.gp0, z.f0), r1 = fma(U.gamma, z.g1 - z.gp1, z.f1);
+    if (sqrt(wsum(pdot(r0, r1, r0, r1))) < U.akkt_tol) return false;
   }
   // update_lipschitz_constant
   {
     double cost_half = eval_cost(g, sm, lane, pb, z.h0, z.h1);
     int it = 0;
     while (true) {
-      const double ip = wsum(z.g0 * z.f0 + z.g1 * z.f1);
+      const double ip = wsum(pdot(z.g0, z.g1, z.f0, z.f1));
       const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - ip +
                          (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
       if (!(cost_half > rhs && it < MAX_LIPSCHITZ_UPDATE_ITERATIONS &&
@@ -192,7 +192,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   } else {
     // linesearch on the forward-backward envelope
     const double e0 = z.s0 - z.h0, e1 = z.s1 - z.h1;
-    double dist2 = e0 * e0 + e1 * e1, gg = z.g0 * z.g0 + z.g1 * z.g1, dummy = 0.0;
+    double dist2 = pdot(e0, e1, e0, e1), gg = pdot(z.g0, z.g1, z.g0, z.g1), dummy = 0.0;
     wsum3(dist2, gg, dummy);
     const double fbe = U.cost - 0.5 * U.gamma * gg + 0.5 * dist2 / U.gamma;
     const double rhs_ls = fbe - U.sigma * (U.norm_fpr * U.norm_fpr);
@@ -201,12 +201,12 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
     double p0, p1;
     while (true) {
       const double one_m = 1.0 - U.tau;
-      p0 = z.u0 - one_m * z.f0 - U.tau * z.d0;
-      p1 = z.u1 - one_m * z.f1 - U.tau * z.d1;
+      p0 = fma(-U.tau, z.d0, fma(-one_m, z.f0, z.u0));
+      p1 = fma(-U.tau, z.d1, fma(-one_m, z.f1, z.u1));
       U.cost = eval_grad(g, sm, lane, pb, p0, p1, z.g0, z.g1);
       gradient_and_half_step(g, z, U, p0, p1);
       const double q0 = z.h0 - z.s0, q1 = z.h1 - z.s1;
-      double dd = q0 * q0 + q1 * q1, g2 = z.g0 * z.g0 + z.g1 * z.g1, dm = 0.0;
+      double dd = pdot(q0, q1, q0, q1), g2 = pdot(z.g0, z.g1, z.g0, z.g1), dm = 0.0;
       wsum3(dd, g2, dm);
       const double lhs_ls = U.cost - 0.5 * U.gamma * g2 + 0.5 * dd / U.gamma;
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
@@ -277,8 +277,9 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
         }
         double t0, t1;
         eval_grad(g, sm, lane, pb, z.u0 + h0, z.u1 + h1, t0, t1);
-        double nh = h0 * h0 + h1 * h1;
-        double nd = (t0 - z.g0) * (t0 - z.g0) + (t1 - z.g1) * (t1 - z.g1);
+        const double e0 = t0 - z.g0, e1 = t1 - z.g1;
+        double nh = pdot(h0, h1, h0, h1);
+        double nd = pdot(e0, e1, e0, e1);
         double dm = 0.0;
         wsum3(nh, nd, dm);
         U.L = sqrt(nd) / sqrt(nh);
@@ -328,7 +329,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     }
     {
       const double da = yp_a - pb.ya, dw = yp_w - pb.yw;
-      delta_y_norm_plus = sqrt(wsum(da * da + dw * dw));
+      delta_y_norm_plus = sqrt(wsum(pdot(da, dw, da, dw)));
     }
     const bool crit1 = alm_iter > 0 && delta_y_norm_plus <= pb.c * g.delta_tol + SMALL_EPSILON;
     const bool crit2 = f2_norm_plus <= g.delta_tol + SMALL_EPSILON;
