@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- batched NMPC solves/sec (BASELINE.json metric) on N B200s of one node.
+
+One "step" = one pass of the hot path over one batch of synthetic scenes:
+solve every scene of the workload once (PANOC + ALM to the reference's tolerances).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      (CPU arm: the oracle on the host cores)
+
+Prints ONE JSON line (rank 0).  Keys: see the contract in the task; extra objects
+`roofline` (FP64 FMA pipe of the solve kernel, peak measured live by a DFMA probe)
+and `cpu_baseline` (oracle port on the host cores, bounded sample).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# FP64 floating-point operations per evaluation of the solve kernel, counted from
+# csrc/ttmpc_device.cuh for the default shapes (N=20 steps, 10 other robots, 10
+# static obstacles x 4 edges, 15 dynamic slots); fma = 2 flops.  See DESIGN.md §kernels.
+def eval_flops(cfg, grad: bool, bodies_per_eval: float) -> float:
+    N, No, Ns, ne, Nd = cfg.N_hor, cfg.Nother, cfg.Nstcobs, cfg.nstcobs // 3, cfg.Ndynobs
+    per_lane = 0.0
+    per_lane += 3 * 34 + 14            # three tt_sincos + rollout combination
+    per_lane += (N + 1) / 2 * 15       # reference path: avg (N+1)/2 segments x 15 flops
+    per_lane += 10                     # speed / control terms
+    per_lane += No * 6                 # fleet: distance test
+    per_lane += Ns * (ne * 6 + 1)      # static: edges + product
+    per_lane += Nd * 5                 # dynamic: bounding test
+    per_lane += 22                     # accelerations + ALM rows
+    if grad:
+        per_lane += 20 + 40            # selected-segment gradient, adjoint combination
+    total = per_lane * N
+    total += 3 * 5 * 32 + 3 * 5 * 32   # wsum3 + three prefix scans (adds on 32 lanes)
+    if grad:
+        total += 3 * 5 * 32            # three suffix scans
+    total += bodies_per_eval * (34 if grad else 22)
+    total += Nd * 4
+    return total
+
+
+def clocks_sampler(stop, out, gpu_index):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                "-i", str(gpu_index)], capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 9:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+    sm = sorted(float(s[1]) for s in samples)
+    reasons = set()
+    for s in samples:
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][2]),
+            "power_w_max": max(float(s[3]) for s in samples), "reasons": sorted(reasons),
+            "samples": len(samples)}
+
+
+def build_workload(name, rank, world):
+    import trajtrack_mpcndqn_rlboost_b200 as t
+    w = t.scenes.WORKLOADS[name]
+    cfg = t.Configurator().to_ttmpc(**w["solver"])
+    # weak scaling: every rank solves its own shard of n scenes (different seed per rank)
+    p = t.scenes.make_scenes(w["n"], cfg, seed=1000 + rank, n_static=w["n_static"],
+                             n_dynamic=w["n_dynamic"], blocking_fraction=w["blocking_fraction"])
+    return cfg, p, w
+
+
+def run_reference_arm(args):
+    """CPU arm: the oracle (port of the OpEn solve, reference operation order) on all
+    host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests import oracle_lib as O
+    cfg, p, w = build_workload(args.workload, 0, 1)
+    cores = os.cpu_count() or 1
+    sample = min(len(p), args.cpu_sample)
+    O.load()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.solve_batch(cfg, p[:sample], threads=cores, warp=False)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": "batched NMPC solves/sec", "value": value, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "scenes_per_step": sample, "N_hor": cfg.N_hor,
+                   "note": "OpEn is Rust and absent here: CPU port (oracle, reference operation "
+                           "order) on all host cores; each step = a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                         "sample": f"first {sample} scenes of {args.workload}, pthreads"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="static4096")
+    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import trajtrack_mpcndqn_rlboost_b200 as t
+    from trajtrack_mpcndqn_rlboost_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg, p_host, w = build_workload(args.workload, rank, world)
+    n = len(p_host)
+    solver = t.BatchSolver(cfg)
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    p_pinned = torch.from_numpy(p_host).pin_memory()
+    p_dev = p_pinned.to(dev, non_blocking=True)
+    bufs = solver.alloc_device(n, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    stream = torch.cuda.current_stream()
+    # ---------------- device-resident leg ("value")
+    solver.read_stats(reset=True)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.warmup + args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.warmup + args.steps)]
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            barrier()
+            solver.read_stats(reset=True)
+            th.start()
+            t_wall0 = time.perf_counter()
+        flush.zero_()                      # L2 flush between timed iterations
+        ev0[it].record(stream)
+        solver.run_device(p_dev, bufs)     # ONE kernel launch (+ one 4-byte memset)
+        ev1[it].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    stop.set()
+    kern_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(args.warmup, args.warmup + args.steps)]
+    stats = solver.read_stats(reset=True)
+    step_ms = max_over_ranks(sum(kern_ms) / len(kern_ms))
+    total_scenes = n * world
+    value = total_scenes / (step_ms * 1e-3)
+    status = bufs["exit_status"].cpu().numpy()
+
+    # ---------------- end-to-end leg ("e2e"): the reference-facing call with HOST buffers,
+    # BatchSolver.run -> ttmpc_solve_batch_host: host parameters -> pinned staging -> H2D,
+    # solve, D2H of every result field, all inside the timed region.
+    e2e_times = []
+    for it in range(2 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        host_sol = solver.run(p_host)
+        dt = time.perf_counter() - t0
+        if it >= 2:
+            e2e_times.append(dt)
+    assert np.array_equal(host_sol.exit_status, status)
+    e2e_step = max_over_ranks(sum(e2e_times) / len(e2e_times))
+    e2e_value = total_scenes / e2e_step
+    h2d = p_host.nbytes
+    N = cfg.N_hor
+    d2h = n * (2 * 2 * N * 8 + 5 * 8 + N * 3 * 8 + 3 * 4 + 2 * 8)
+
+    # ---------------- roofline of the solve kernel: FP64 FMA pipe
+    peak = C.c_double()
+    _lib.check(lib.ttmpc_measure_fp64_peak(C.byref(peak), None), "fp64 peak probe")
+    steps = args.steps
+    n_cost = stats["cost_evals"] / steps
+    n_grad = stats["grad_evals"] / steps
+    bodies = stats["dyn_bodies"] / max(1.0, (stats["cost_evals"] + stats["grad_evals"]))
+    flops = n_cost * eval_flops(cfg, False, bodies) + n_grad * eval_flops(cfg, True, bodies)
+    local_ms = sum(kern_ms) / len(kern_ms)
+    achieved = flops / (local_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                "peak_source": "measured live: DFMA probe kernel (ttmpc_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "hbm_GBps_algorithmic": (p_host.nbytes + d2h) / (local_ms * 1e-3) / 1e9,
+                "evals_per_solve": (n_cost + n_grad) / n,
+                "panoc_iters_per_solve": stats["panoc_iters"] / steps / n}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): oracle port on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_lib as O
+        cores = os.cpu_count() or 1
+        sample = min(n, args.cpu_sample)
+        O.load()
+        t0 = time.perf_counter()
+        O.solve_batch(cfg, p_host[:sample], threads=cores, warp=False)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} scenes of {args.workload}, {dt:.1f} s, pthreads"}
+
+    if rank == 0:
+        info = solver.launch_info(n)
+        line = {
+            "metric": "batched NMPC solves/sec", "value": value, "unit": "solves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "scenes_per_gpu": n, "N_hor": cfg.N_hor,
+                       "Nstcobs": cfg.Nstcobs, "Ndynobs": cfg.Ndynobs, "static_per_scene": w["n_static"],
+                       "dynamic_per_scene": w["n_dynamic"], "max_inner": cfg.max_inner_iterations,
+                       "max_outer": cfg.max_outer_iterations, "l2": "flushed (256 MB write) between iterations",
+                       "parallelism": f"scenes sharded, {world} rank(s), no collective in the solve",
+                       "launch": info},
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step * 1e3},
+            "gpu_launches": args.steps,
+            "clocks": summarize_clocks(samples),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "exit_status_hist": np.bincount(status, minlength=4).tolist(),
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1089,9 +1089,11 @@ static int solve_mode(const ttmpc_config *g, const double *p, double *u, double 
     int crit3 = pc->akkt_tol <= g->tolerance + SMALL_EPSILON;
     if (crit1 && crit2 && crit3) { exit_status = inner_status; break; }
     /* penalty stall criterion */
-    int stall = alm_iter == 0 ||
-                delta_y_norm_plus <= g->sufficient_decrease_coeff * delta_y_norm + SMALL_EPSILON ||
-                f2_norm_plus <= g->sufficient_decrease_coeff * f2_norm + SMALL_EPSILON;
+    /* is_penalty_stall_criterion: iteration 0, or BOTH infeasibilities (ALM rows and
+       penalty rows; n1 > 0 and n2 > 0 here) decreased sufficiently */
+    int crit_alm = delta_y_norm_plus <= g->sufficient_decrease_coeff * delta_y_norm + SMALL_EPSILON;
+    int crit_pm = n2 == 0 || f2_norm_plus <= g->sufficient_decrease_coeff * f2_norm + SMALL_EPSILON;
+    int stall = alm_iter == 0 || (crit_alm && crit_pm);
     if (!stall) pb.c *= g->penalty_update_factor;
     /* inner tolerance update */
     pc_set_akkt(pc, fmax(pc->akkt_tol * g->inner_tolerance_update_factor, g->tolerance));

@@ -335,9 +335,10 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     const bool crit2 = f2_norm_plus <= g.delta_tol + SMALL_EPSILON;
     const bool crit3 = U.akkt_tol <= g.tol + SMALL_EPSILON;
     if (crit1 && crit2 && crit3) { exit_status = inner_status; break; }
-    const bool stall = alm_iter == 0 ||
-                       delta_y_norm_plus <= g.suff_dec * delta_y_norm + SMALL_EPSILON ||
-                       f2_norm_plus <= g.suff_dec * f2_norm + SMALL_EPSILON;
+    // is_penalty_stall_criterion: iteration 0, or both infeasibilities decreased enough
+    const bool crit_alm = delta_y_norm_plus <= g.suff_dec * delta_y_norm + SMALL_EPSILON;
+    const bool crit_pm = g.Ndyn == 0 || f2_norm_plus <= g.suff_dec * f2_norm + SMALL_EPSILON;
+    const bool stall = alm_iter == 0 || (crit_alm && crit_pm);
     if (!stall) pb.c *= g.pen_factor;
     U.akkt_tol = fmax(U.akkt_tol * g.tol_factor, g.tol);
     z.gp0 = 0.0; z.gp1 = 0.0;  // set_akkt_tolerance allocates a fresh zero vector

@@ -31,7 +31,7 @@ def _rect_halfspaces(cx, cy, hx, hy, ang):
 
 
 def make_scenes(n: int, cfg: TtmpcConfig, seed: int = 0, n_static: int = 4, n_dynamic: int = 0,
-                mode_speed: float = 1.2, blocking_fraction: float = 0.5, mpc: Configurator = None):
+                mode_speed: float = 1.2, blocking_fraction: float = 0.1, mpc: Configurator = None):
     """Returns p [n, np] float64 (and a dict with the pieces, for tests)."""
     rng = np.random.default_rng(seed)
     mpc = mpc or Configurator()
@@ -121,8 +121,8 @@ def make_scenes(n: int, cfg: TtmpcConfig, seed: int = 0, n_static: int = 4, n_dy
 
 WORKLOADS = {
     # BASELINE.json configs[1]: 4096 scenes, default horizon, static polygon obstacles
-    "static4096": dict(n=4096, n_static=4, n_dynamic=0, solver={}),
+    "static4096": dict(n=4096, n_static=4, n_dynamic=0, blocking_fraction=0.1, solver={}),
     # configs[2] per-GPU shard: moving ellipses, long iteration limits
-    "dynamic8192": dict(n=8192, n_static=3, n_dynamic=4,
+    "dynamic8192": dict(n=8192, n_static=3, n_dynamic=4, blocking_fraction=0.1,
                         solver=dict(max_inner_iterations=2000, max_outer_iterations=20)),
 }
