@@ -221,7 +221,7 @@ def main():
     e2e_value = total_scenes / e2e_step
     h2d = p_host.nbytes
     N = cfg.N_hor
-    d2h = n * (2 * 2 * N * 8 + 5 * 8 + N * 3 * 8 + 3 * 4 + 2 * 8)
+    d2h = n * (2 * 2 * N * 8 + 5 * 8 + N * 3 * 8 + 3 * 4 + 4 * 8)
 
     # ---------------- roofline of the solve kernel: FP64 FMA pipe
     peak = C.c_double()

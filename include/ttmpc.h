@@ -126,7 +126,8 @@ typedef struct ttmpc_result {
   double *penalty;      /* [n]  final c                                             */
   double *y;            /* [n][2*N] in: initial multipliers (see use_y0), out: final */
   double *pred_states;  /* [n][N][ns] rollout of u* from p.s (trajectory_generator.py:296-301) */
-  long long *evals;     /* [n][2] number of (cost-only, cost+gradient) evaluations  */
+  long long *evals;     /* [n][4] cost-only evals, cost+gradient evals, solve time [ns],
+                           solve start [ns, %globaltimer] (diagnostics)              */
 } ttmpc_result;
 
 /* ------------------------------------------------------------------------
@@ -229,6 +230,10 @@ int ttmpc_read_stats(unsigned long long out[4], int reset);
 /* Launch geometry the solve kernel uses for n_scenes (reporting only). */
 int ttmpc_launch_info(const ttmpc_config *cfg, int n_scenes, int *grid, int *block,
                       int *smem_bytes, int *blocks_per_sm, int *sm_count);
+
+/* Single-warp latency probe (diagnostics): cycles per call of {cost eval, gradient
+ * eval, butterfly sum, L-BFGS apply, fp64 divide, sqrt, dependent DFMA, checksum}. */
+int ttmpc_probe_latency(const ttmpc_config *cfg, const double *h_p, long long out[8], int reps);
 
 /* FP64 FMA-pipe peak probe: runs a dependent-chain-free DFMA kernel on every
  * SM and returns achieved TFLOP/s (used by bench.py as the roofline

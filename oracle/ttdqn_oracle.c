@@ -138,7 +138,7 @@ void ttdqn_oracle_observe(const ttdqn_scene_layout *lay, const double *agent,
 static float normalize_distance_f32(float d, float max_distance) {
   float t = -2.0f * d;
   t = t / max_distance;
-  t = expf(t);
+  t = (float)exp((double)t); /* correctly rounded fp32 exp on both sides */
   t = 1.0f + t;
   t = 2.0f / t;
   return t - 1.0f;

@@ -501,7 +501,8 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
                      double c, const double *y, double *grad, double *st_out) {
   const offs_t o = offsets(g);
   const int N = g->N_hor, ne = g->nstcobs / 3, GRAD = grad != NULL;
-  const double ts = g->ts, h6 = g->ts / 6.0, veh_d2 = g->vehicle_width * g->vehicle_width;
+  const double ts = g->ts, inv_ts = 1.0 / g->ts, h6 = g->ts / 6.0,
+               veh_d2 = g->vehicle_width * g->vehicle_width;
   const double *s = p + o.s, *q = p + o.q;
   const double x0 = s[0], y0 = s[1], th0 = s[2], xg = s[3], yg = s[4], thg = s[5];
   const double v_init = s[6], w_init = s[7];
@@ -657,12 +658,12 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
     /* accelerations + ALM */
     {
       const double vp = k ? v[k - 1] : v_init, wp = k ? w[k - 1] : w_init;
-      aa[k] = (v[k] - vp) / ts; aw[k] = (w[k] - wp) / ts;
+      aa[k] = (v[k] - vp) * inv_ts; aw[k] = (w[k] - wp) * inv_ts;
       cost[k] += fma(aw[k] * aw[k], wacc_pen, (aa[k] * aa[k]) * acc_pen);
-      const double cm = fmax(c, 1.0);
-      double z = aa[k] + (y ? y[k] : 0.0) / cm;
+      const double icm = 1.0 / fmax(c, 1.0);
+      double z = fma(y ? y[k] : 0.0, icm, aa[k]);
       ea[k] = z - clip(z, g->lin_acc_min, g->lin_acc_max);
-      z = aw[k] + (y ? y[N + k] : 0.0) / cm;
+      z = fma(y ? y[N + k] : 0.0, icm, aw[k]);
       ew[k] = z - clip(z, -g->ang_acc_max, g->ang_acc_max);
       alm[k] = fma(ew[k], ew[k], ea[k] * ea[k]);
     }
@@ -726,8 +727,8 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
       const double ea_n = last ? 0.0 : ea[k + 1], ew_n = last ? 0.0 : ew[k + 1];
       double dv = 2 * qvel * (v[k] - vr[k]) + 2 * rv * v[k];
       double dw = 2 * rw * w[k];
-      dv += 2 * acc_pen * (aa[k] - aa_n) / ts + c * (ea[k] - ea_n) / ts;
-      dw += 2 * wacc_pen * (aw[k] - aw_n) / ts + c * (ew[k] - ew_n) / ts;
+      dv += (2 * acc_pen * (aa[k] - aa_n) + c * (ea[k] - ea_n)) * inv_ts;
+      dw += (2 * wacc_pen * (aw[k] - aw_n) + c * (ew[k] - ew_n)) * inv_ts;
       grad[2 * k] = dv + lx[k] * dxdv + ly[k] * dydv;
       grad[2 * k + 1] = dw + lx[k] * dxdw + ly[k] * dydw + lt[k] * ts;
     }
@@ -1058,9 +1059,10 @@ static int solve_mode(const ttmpc_config *g, const double *p, double *u, double 
       pb.n_cost++;
       f2_norm_plus = sqrt(e.f2sq);
       f_final = e.f;
+      const double inv_ts = 1.0 / g->ts;
       for (int k = 0; k < N; k++) {
-        w1[k] = (u[2 * k] - (k ? u[2 * (k - 1)] : p[6])) / g->ts;
-        w1[N + k] = (u[2 * k + 1] - (k ? u[2 * (k - 1) + 1] : p[7])) / g->ts;
+        w1[k] = (u[2 * k] - (k ? u[2 * (k - 1)] : p[6])) * inv_ts;
+        w1[N + k] = (u[2 * k + 1] - (k ? u[2 * (k - 1) + 1] : p[7])) * inv_ts;
       }
     } else {
       ttmpc_oracle_eval(g, u, p, &f_final, w1, w2);
@@ -1070,7 +1072,8 @@ static int solve_mode(const ttmpc_config *g, const double *p, double *u, double 
     for (int i = 0; i < n1; i++) {
       double lo = i < N ? g->lin_acc_min : -g->ang_acc_max;
       double hi = i < N ? g->lin_acc_max : g->ang_acc_max;
-      double t = clip(w1[i] + y[i] / fmax(pb.c, 1.0), lo, hi);
+      double t = warp ? clip(fma(y[i], 1.0 / fmax(pb.c, 1.0), w1[i]), lo, hi)
+                      : clip(w1[i] + y[i] / fmax(pb.c, 1.0), lo, hi);
       y_plus[i] = y[i] + pb.c * (w1[i] - t);
     }
     if (warp) { /* lane k pairs the k-th linear and angular rows */
@@ -1176,7 +1179,7 @@ static void batch_range(job_t *jb) {
         ttmpc_oracle_rollout(g, u, jb->p + (size_t)i * np, r->pred_states + (size_t)i * N * 3);
       }
     }
-    if (r->evals) { r->evals[2 * i] = st.n_cost_evals; r->evals[2 * i + 1] = st.n_grad_evals; }
+    if (r->evals) { r->evals[4 * i] = st.n_cost_evals; r->evals[4 * i + 1] = st.n_grad_evals; r->evals[4 * i + 2] = 0; r->evals[4 * i + 3] = 0; }
   }
 }
 

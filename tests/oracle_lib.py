@@ -113,7 +113,7 @@ def solve_batch(cfg, p, u0=None, y0=None, c0=None, threads=1, warp=False):
     c0a = None if c0 is None else np.ascontiguousarray(np.broadcast_to(np.asarray(c0, np.float64), (n,)))
     out = dict(cost=np.zeros(n), exit_status=np.zeros(n, np.int32), outer=np.zeros(n, np.int32),
                inner=np.zeros(n, np.int32), fpr=np.zeros(n), f1=np.zeros(n), f2=np.zeros(n),
-               pen=np.zeros(n), pred=np.zeros((n, N, 3)), evals=np.zeros((n, 2), np.int64))
+               pen=np.zeros(n), pred=np.zeros((n, N, 3)), evals=np.zeros((n, 4), np.int64))
     res = TtmpcResult(u=_p(u), cost=_p(out["cost"]), exit_status=_p(out["exit_status"]),
                       outer_iters=_p(out["outer"]), inner_iters=_p(out["inner"]), last_fpr=_p(out["fpr"]),
                       f1_infeas=_p(out["f1"]), f2_norm=_p(out["f2"]), penalty=_p(out["pen"]), y=_p(y),

@@ -1,0 +1,18 @@
+"""Tiny driver for ncu: solve the static4096 workload a few times on device."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import trajtrack_mpcndqn_rlboost_b200 as t
+name = sys.argv[1] if len(sys.argv) > 1 else "static4096"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+w = t.scenes.WORKLOADS[name]
+cfg = t.Configurator().to_ttmpc(**w["solver"])
+p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
+                         blocking_fraction=w["blocking_fraction"])
+s = t.BatchSolver(cfg)
+dp = torch.from_numpy(p).cuda()
+bufs = s.alloc_device(len(p))
+for _ in range(reps):
+    s.run_device(dp, bufs)
+torch.cuda.synchronize()
+print("done", s.read_stats())

@@ -95,7 +95,7 @@ __device__ __forceinline__ double ray_seg_hit(double ax, double ay, double rx, d
 __device__ __forceinline__ float normalize_distance_f32(float d, float max_distance) {
   float t = -2.0f * d;
   t = t / max_distance;
-  t = expf(t);
+  t = (float)exp((double)t); /* correctly rounded fp32 exp on both sides */
   t = 1.0f + t;
   t = 2.0f / t;
   return t - 1.0f;

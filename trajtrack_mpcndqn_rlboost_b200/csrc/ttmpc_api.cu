@@ -81,8 +81,8 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   g->off_qdyn = g->off_od + c->Ndynobs * c->ndynobs * N + N;
   g->np = g->off_qdyn + N;
   g->warps_per_block = 4;
-  g->smem_per_warp = smem_bytes_per_warp(N, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
-  g->ts = c->ts; g->h6 = c->ts / 6.0; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;
+  g->smem_per_warp = smem_bytes_per_warp(N, g->Nother, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
+  g->ts = c->ts; g->inv_ts = 1.0 / c->ts; g->h6 = c->ts / 6.0; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;
   g->vmin = c->lin_vel_min; g->vmax = c->lin_vel_max; g->wmax = c->ang_vel_max;
   g->amin = c->lin_acc_min; g->amax = c->lin_acc_max; g->awmax = c->ang_acc_max;
   g->tol = c->tolerance; g->init_tol = c->initial_tolerance; g->delta_tol = c->delta_tolerance;
@@ -247,7 +247,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   if (n == 0) return TTMPC_OK;
   const size_t nn = (size_t)n, nu = 2 * (size_t)g.N;
   size_t total = 4096 + 256 * 16 + sizeof(double) * (nn * g.np + nn + 2 * nn * nu + 5 * nn + nn * g.N * 3) +
-                 sizeof(int) * 3 * nn + sizeof(long long) * 2 * nn;
+                 sizeof(int) * 3 * nn + sizeof(long long) * 4 * nn;
   Workspace *w;
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -274,7 +274,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   cv.take(nn, &dex, &hex);
   cv.take(nn, &dout, &hout);
   cv.take(nn, &din, &hin);
-  cv.take(2 * nn, &dev, &hev);
+  cv.take(4 * nn, &dev, &hev);
   cudaStream_t st = 0;
   std::memcpy(hp, h_p, sizeof(double) * nn * g.np);
   CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * nn * g.np, cudaMemcpyHostToDevice, st));
@@ -314,7 +314,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   if (res->exit_status) std::memcpy(res->exit_status, hex, sizeof(int) * nn);
   if (res->outer_iters) std::memcpy(res->outer_iters, hout, sizeof(int) * nn);
   if (res->inner_iters) std::memcpy(res->inner_iters, hin, sizeof(int) * nn);
-  if (res->evals) std::memcpy(res->evals, hev, sizeof(long long) * 2 * nn);
+  if (res->evals) std::memcpy(res->evals, hev, sizeof(long long) * 4 * nn);
   return TTMPC_OK;
 }
 
@@ -384,6 +384,24 @@ extern "C" int ttmpc_eval_batch_host(const ttmpc_config *cfg, int n, const doubl
   if (h_psi) TRY_OR_CLEAN(cudaMemcpy(h_psi, dpsi, sizeof(double) * nn, cudaMemcpyDeviceToHost));
   if (h_grad) TRY_OR_CLEAN(cudaMemcpy(h_grad, dgrad, sizeof(double) * nn * nu, cudaMemcpyDeviceToHost));
   cleanup();
+  return TTMPC_OK;
+}
+
+// Latency probe (diagnostics): h_p = one scene's parameters (host); out[8] cycles of
+// {cost eval, grad eval, wsum, lbfgs apply (mem pairs), div, sqrt, dfma, checksum}.
+extern "C" int ttmpc_probe_latency(const ttmpc_config *cfg, const double *h_p, long long out[8], int reps) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  double *dp = nullptr, *dyn = nullptr; long long *dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dp, sizeof(double) * g.np));
+  CUDA_TRY(cudaMalloc(&dyn, sizeof(double) * DYN_FIELDS * (g.Ndyn > 0 ? g.Ndyn : 1) * g.N));
+  CUDA_TRY(cudaMalloc(&dout, 64));
+  CUDA_TRY(cudaMemcpy(dp, h_p, sizeof(double) * g.np, cudaMemcpyHostToDevice));
+  CUDA_TRY(launch_probe(g, dp, dyn, dout, reps, 0));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, dout, 64, cudaMemcpyDeviceToHost));
+  cudaFree(dp); cudaFree(dyn); cudaFree(dout);
   return TTMPC_OK;
 }
 

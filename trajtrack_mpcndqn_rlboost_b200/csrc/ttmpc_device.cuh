@@ -37,7 +37,7 @@ struct DevCfg {
   int off_s, off_q, off_r, off_vref, off_c, off_os, off_od, off_qdyn, np;
   int smem_per_warp;  // bytes
   int warps_per_block;
-  double ts, h6, veh_d2, margin;
+  double ts, inv_ts, h6, veh_d2, margin;
   double vmin, vmax, wmax, amin, amax, awmax;
   double tol, init_tol, delta_tol, c0, pen_factor, tol_factor, suff_dec;
 };
@@ -74,12 +74,13 @@ __host__ __device__ __forceinline__ void tt_sincos(double x, double *s, double *
 }
 
 // ---------------------------------------------------------------- warp utils
-__device__ __forceinline__ double wsum(double v) {
+static __device__ __noinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-__device__ __forceinline__ void wsum3(double &a, double &b, double &c) {
+struct D3 { double a, b, c; };
+static __device__ __noinline__ D3 wsum3v(double a, double b, double c) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ta = __shfl_xor_sync(FULL, a, o);
@@ -87,6 +88,12 @@ __device__ __forceinline__ void wsum3(double &a, double &b, double &c) {
     double tc = __shfl_xor_sync(FULL, c, o);
     a += ta; b += tb; c += tc;
   }
+  D3 r; r.a = a; r.b = b; r.c = c;
+  return r;
+}
+__device__ __forceinline__ void wsum3(double &a, double &b, double &c) {
+  const D3 r = wsum3v(a, b, c);
+  a = r.a; b = r.b; c = r.c;
 }
 // inclusive prefix sum over lanes (Kogge-Stone)
 __device__ __forceinline__ double wscan(double v, int lane) {
@@ -123,25 +130,46 @@ struct WarpCtx {
   double x0, y0, th0, xg, yg, thg, v_init, w_init;
   double qvel, rv, rw, qN, qthetaN, qrpd, acc_pen, wacc_pen;
   long long n_cost, n_grad, n_body;  // evaluation counters (lane 0 view)
+  int nstc_active;                   // static obstacles that can ever be non-zero
 };
 
 struct WarpSmem {
   WarpCtx *ctx;
-  double *seg;   // [5][N]: s1x s1y sx sy inv_den
-  double *os;    // [Nstc*nstcobs] per obstacle: b[ne], -a0[ne], -a1[ne]
-  double *D;     // [Ndyn] per-obstacle hard sums of the last evaluation
-  double2 *lbs;  // [(mem+1)][N]
-  double2 *lby;  // [(mem+1)][N]
-  double *rho;   // [mem+1]
-  double *alpha; // [mem]
+  double *seg;    // [5][N]: s1x s1y sx sy inv_den
+  double *os;     // [Nstc*nstcobs] per obstacle: b[ne], -a0[ne], -a1[ne]
+  double *D;      // [Ndyn] per-obstacle hard sums of the last evaluation
+  double *vref;   // [N] speed reference
+  double2 *fleet; // [Nother][N] other robots' (x, y) at each step
+  float4 *dynb;   // [Ndyn][N] conservative fp32 bounding test: cx cy R2 -
+  double2 *lbs;   // [(mem+1)][N]
+  double2 *lby;   // [(mem+1)][N]
+  double *rho;    // [mem+1]
+  double *alpha;  // [mem]
 };
 
-__host__ __device__ inline int smem_bytes_per_warp(int N, int Nstc, int nstcobs, int Ndyn, int mem) {
+// Compile-time problem dimensions (0 = take the value from DevCfg at run time).
+// The default configuration (config/mpc_default.yaml) gets a fully specialised kernel.
+template <int N_, int NO_, int NS_, int NE_, int ND_>
+struct Dims {
+  __device__ __forceinline__ static int N(const DevCfg &g) { return N_ ? N_ : g.N; }
+  __device__ __forceinline__ static int Nother(const DevCfg &g) { return N_ ? NO_ : g.Nother; }
+  __device__ __forceinline__ static int Nstc(const DevCfg &g) { return N_ ? NS_ : g.Nstc; }
+  __device__ __forceinline__ static int ne(const DevCfg &g) { return N_ ? NE_ : g.ne; }
+  __device__ __forceinline__ static int Ndyn(const DevCfg &g) { return N_ ? ND_ : g.Ndyn; }
+};
+using DimsRuntime = Dims<0, 0, 0, 0, 0>;
+using DimsDefault = Dims<20, 10, 10, 4, 15>;
+
+__host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, int nstcobs, int Ndyn,
+                                                   int mem) {
   size_t b = 0;
   b += (sizeof(WarpCtx) + 15) / 16 * 16;
   b += sizeof(double) * 5 * N;
-  b += sizeof(double) * Nstc * nstcobs;
+  b += sizeof(double) * ((Nstc * nstcobs + 1) / 2 * 2);
   b += sizeof(double) * ((Ndyn + 1) / 2 * 2);
+  b += sizeof(double) * ((N + 1) / 2 * 2);
+  b += sizeof(double2) * (size_t)Nother * N;
+  b += sizeof(float4) * (size_t)Ndyn * N;
   b += sizeof(double2) * (size_t)(mem + 1) * N * 2;
   b += sizeof(double) * ((mem + 2) / 2 * 2);
   b += sizeof(double) * ((mem + 1) / 2 * 2);
@@ -154,9 +182,12 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
   w.ctx = reinterpret_cast<WarpCtx *>(q); q += (sizeof(WarpCtx) + 15) / 16 * 16;
   w.lbs = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * g.N;
   w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * g.N;
+  w.fleet = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.Nother * g.N;
+  w.dynb = reinterpret_cast<float4 *>(q); q += sizeof(float4) * (size_t)g.Ndyn * g.N;
   w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 5 * g.N;
-  w.os = reinterpret_cast<double *>(q); q += sizeof(double) * g.Nstc * g.nstcobs;
+  w.os = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.Nstc * g.nstcobs + 1) / 2 * 2);
   w.D = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.Ndyn + 1) / 2 * 2);
+  w.vref = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.N + 1) / 2 * 2);
   w.rho = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.mem + 2) / 2 * 2);
   w.alpha = reinterpret_cast<double *>(q);
   return w;
@@ -195,12 +226,38 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     sm.seg[2 * g.N + j] = sx;  sm.seg[3 * g.N + j] = sy;
     sm.seg[4 * g.N + j] = 1.0 / den;
   }
-  // static half-spaces: keep b, store -a0 and -a1 (res = b + (-a0) x + (-a1) y)
+  // static half-spaces: keep b, store -a0 and -a1 (res = b + (-a0) x + (-a1) y).
+  // An obstacle with an edge a0 = a1 = 0, b <= 0 (e.g. a zero-padded slot) has
+  // max(0, res) = 0 on that edge for every position, so its product is exactly 0:
+  // such obstacles are dropped here (same order for the rest), which changes no result.
   const double *os = p + g.off_os;
-  for (int i = lane; i < g.Nstc * g.nstcobs; i += 32) {
-    const int e = i % g.nstcobs;
-    sm.os[i] = (e < g.ne) ? os[i] : -os[i];
+  {
+    int n_act = 0;
+    for (int i0 = 0; i0 < g.Nstc; i0 += 32) {
+      const int i = i0 + lane;
+      bool live = false;
+      if (i < g.Nstc) {
+        live = true;
+        const double *b = os + i * g.nstcobs, *a0 = b + g.ne, *a1 = b + 2 * g.ne;
+        for (int e = 0; e < g.ne; e++)
+          if (a0[e] == 0.0 && a1[e] == 0.0 && !(b[e] > 0.0)) live = false;
+      }
+      const unsigned m = __ballot_sync(FULL, live);
+      if (live) {
+        const int slot = n_act + __popc(m & ((1u << lane) - 1u));
+        const double *src = os + i * g.nstcobs;
+        double *dst = sm.os + slot * g.nstcobs;
+        for (int e = 0; e < g.nstcobs; e++) dst[e] = (e < g.ne) ? src[e] : -src[e];
+      }
+      n_act += __popc(m);
+    }
+    if (lane == 0) c->nstc_active = n_act;
   }
+  for (int k = lane; k < g.N; k += 32) sm.vref[k] = p[g.off_vref + k];
+  // other robots: c is robot-major, (x y theta) per step (mpc_generator.py:207-209)
+  const double *cpar = p + g.off_c;
+  for (int t = lane; t < g.Nother * g.N; t += 32)
+    sm.fleet[t] = make_double2(cpar[(size_t)t * 3], cpar[(size_t)t * 3 + 1]);
   // dynamic obstacle table
   const double *od = p + g.off_od, *qdyn = p + g.off_qdyn;
   const int npair = g.Ndyn * g.N;
@@ -223,6 +280,16 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     dynf(dyn_scratch, g, 7, j, k) = 1.0 / (Rxm * Rxm);
     dynf(dyn_scratch, g, 8, j, k) = 1.0 / (Rym * Rym);
     dynf(dyn_scratch, g, 9, j, k) = alpha * qdyn[k];
+    // conservative fp32 copy of the bounding test: the radius is padded by the worst
+    // rounding of the fp32 centre / position (8 ulp_f32 of the coordinates) so a pair the
+    // exact fp64 test accepts is never rejected here; rejected pairs contribute exactly 0
+    {
+      const double pad = 4.8e-7 * (fabs(cx) + fabs(cy) + 2.0 * rmax + 1.0) + 1e-6;
+      const double rp = rmax + pad;
+      float r2f = __double2float_ru(rp * rp * (1.0 + 1e-6));
+      if (!(rmax == rmax) || !(cx == cx) || !(cy == cy)) r2f = 0.0f;  // NaN input: exact test is false too
+      sm.dynb[t] = make_float4((float)cx, (float)cy, r2f, 0.0f);
+    }
   }
   __syncwarp();
 }
@@ -232,22 +299,28 @@ struct EvalOut {
   double psi;   // f + c/2 dist^2_C(F1 + y/max(c,1)) + c/2 |F2|^2
   double f;     // original cost (psi at c = 0)
   double f2sq;  // |F2|^2
-  double S;     // static hard sum (F2_j = S + D_j, D in smem)
+  double S;     // static hard sum (F2_j = S + D_j, D in smem when any_hard, else 0)
   double gv, gw;  // this lane's gradient entries (GRAD only)
+  bool any_hard;
 };
 
 // Evaluate psi (and its gradient when GRAD) at this lane's (v, w).
 // ya / yw are this lane's multipliers for the linear / angular acceleration rows.
-template <bool GRAD>
+// DM carries the problem dimensions (compile-time for the default configuration).
+// GRAD is a run-time (warp-uniform) flag: one copy of the code serves both uses, which
+// keeps the hot loop inside the instruction cache.
+template <class DM>
 __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_base, double v,
                                          double w, double c, double ya, double yw,
-                                         double *st_out) {
+                                         double *st_out, const bool GRAD) {
   const DevCfg &g = *gp;
   const WarpSmem sm = carve(smem_base, g);
   const int lane = threadIdx.x & 31;
   double gv = 0.0, gw = 0.0;
   const WarpCtx *cx = sm.ctx;
-  const int N = g.N;
+  const int N = DM::N(g), Nother = DM::Nother(g), Nstc = cx->nstc_active, ne = DM::ne(g),
+            Ndyn = DM::Ndyn(g);
+  const int nstcobs = 3 * ne;
   const bool act = lane < N;
   const double ts = g.ts;
 
@@ -266,8 +339,16 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   const double Cs = fma(4.0, cb, ca) + cc, Ss = fma(4.0, sb, sa) + sc;
   const double hv = g.h6 * v;
   const double dx = hv * Cs, dy = hv * Ss;
-  const double X = cx->x0 + wscan(dx, lane);
-  const double Y = cx->y0 + wscan(dy, lane);
+  double X, Y;
+  {  // two prefix scans, interleaved
+    double a = dx, b = dy;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double ta = __shfl_up_sync(FULL, a, o), tb = __shfl_up_sync(FULL, b, o);
+      if (lane >= o) { a += ta; b += tb; }
+    }
+    X = cx->x0 + a; Y = cx->y0 + b;
+  }
   const double TH = cx->th0 + th_in;
   if (st_out && act) { st_out[3 * lane] = X; st_out[3 * lane + 1] = Y; st_out[3 * lane + 2] = TH; }
 
@@ -278,17 +359,16 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   // ---- reference-path deviation (l.124-139, 202): min over the remaining segments
   {
     double dmin = 0.0; int jmin = lane;
+#pragma unroll 5
     for (int j = 0; j < N; j++) {
       const double s1x = sm.seg[j], s1y = sm.seg[N + j], sx = sm.seg[2 * N + j],
                    sy = sm.seg[3 * N + j], inv = sm.seg[4 * N + j];
-      if (j >= lane) {
-        const double px = X - s1x, py = Y - s1y;
-        const double t_hat = fma(py, sy, px * sx) * inv;
-        const double t = fmin(fmax(t_hat, 0.0), 1.0);
-        const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
-        const double d2 = fma(qy, qy, qx * qx);
-        if (j == lane || !(dmin <= d2)) { dmin = d2; jmin = j; }
-      }
+      const double px = X - s1x, py = Y - s1y;
+      const double t_hat = fma(py, sy, px * sx) * inv;
+      const double t = fmin(fmax(t_hat, 0.0), 1.0);
+      const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
+      const double d2 = fma(qy, qy, qx * qx);
+      if (j >= lane && (j == lane || !(dmin <= d2))) { dmin = d2; jmin = j; }
     }
     if (act) {
       cost = dmin * cx->qrpd;
@@ -310,18 +390,18 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   // ---- speed reference + control action (l.203-204)
   double vr = 0.0;
   if (act) {
-    vr = cx->p[g.off_vref + lane];
+    vr = sm.vref[lane];
     const double dv_ = v - vr;
     cost += cx->qvel * (dv_ * dv_);
     cost += fma(cx->rw, w * w, cx->rv * (v * v));
   }
   // ---- fleet collision (l.207-211)
   if (act) {
-    const double *cp = cx->p + g.off_c + 3 * lane;
     double acc = 0.0, fx = 0.0, fy = 0.0;
-    for (int j = 0; j < g.Nother; j++) {
-      const double ox = cp[(size_t)j * 3 * N], oy = cp[(size_t)j * 3 * N + 1];
-      const double ex = X - ox, ey = Y - oy;
+#pragma unroll 5
+    for (int j = 0; j < Nother; j++) {
+      const double2 o = sm.fleet[j * N + lane];
+      const double ex = X - o.x, ey = Y - o.y;
       const double e = g.veh_d2 - fma(ey, ey, ex * ex);
       if (e > 0.0) {
         acc += e;
@@ -331,55 +411,82 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     cost += 1000.0 * acc;
     if (GRAD) { gx = fma(1000.0, fx, gx); gy = fma(1000.0, fy, gy); }
   }
-  // ---- dynamic obstacles (l.225-237): hard penalty D_j and soft cost
-  unsigned hard_mask_lo = 0, hard_mask_hi = 0;  // obstacles with a positive hard term
+  // ---- dynamic obstacles (l.225-237): hard penalty D_j and soft cost.
+  //      fp32 bounding test from shared memory first; the exact fp64 body (global
+  //      table) only runs for pairs that can be non-zero.
+  unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
   {
     const double *T = cx->dyn;
+    const float Xf = (float)X, Yf = (float)Y;
     double soft = 0.0;
     int bodies = 0;
-    for (int j = 0; j < g.Ndyn; j++) {
-      bool pass = false;
-      double ex = 0.0, ey = 0.0;
+#pragma unroll 5
+    for (int j = 0; j < Ndyn; j++) {
+      bool maybe = false;
       if (act) {
-        ex = X - T[((size_t)0 * g.Ndyn + j) * N + lane];
-        ey = Y - T[((size_t)1 * g.Ndyn + j) * N + lane];
-        pass = fma(ey, ey, ex * ex) < T[((size_t)2 * g.Ndyn + j) * N + lane];
+        const float4 b = sm.dynb[j * N + lane];
+        const float exf = Xf - b.x, eyf = Yf - b.y;
+        maybe = (exf * exf + eyf * eyf) < b.z;
       }
-      double in1 = 0.0;
-      if (pass) {
-        bodies++;
-        const double ca_ = T[((size_t)3 * g.Ndyn + j) * N + lane];
-        const double sa_ = T[((size_t)4 * g.Ndyn + j) * N + lane];
-        const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
-        const double A2 = A * A, B2 = B * B;
-        in1 = fma(-B2, T[((size_t)6 * g.Ndyn + j) * N + lane],
-                  fma(-A2, T[((size_t)5 * g.Ndyn + j) * N + lane], 1.0));
-        const double iRxm = T[((size_t)7 * g.Ndyn + j) * N + lane];
-        const double iRym = T[((size_t)8 * g.Ndyn + j) * N + lane];
-        const double in2 = fma(-B2, iRym, fma(-A2, iRxm, 1.0));
-        if (in2 > 0.0) {
-          const double ws = T[((size_t)9 * g.Ndyn + j) * N + lane];
-          soft = fma(in2 * in2, ws, soft);
-          if (GRAD) {
-            const double wg = ws * (2.0 * in2);
-            const double tA = A * iRxm, tB = B * iRym;
-            gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
-            gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);
+      if (maybe) {
+        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lane];
+        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lane];
+        if (fma(ey, ey, ex * ex) < T[((size_t)2 * Ndyn + j) * N + lane]) {
+          bodies++;
+          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lane];
+          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lane];
+          const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
+          const double A2 = A * A, B2 = B * B;
+          const double in1 = fma(-B2, T[((size_t)6 * Ndyn + j) * N + lane],
+                                 fma(-A2, T[((size_t)5 * Ndyn + j) * N + lane], 1.0));
+          if (in1 > 0.0) hard_mask |= 1ull << j;
+          const double iRxm = T[((size_t)7 * Ndyn + j) * N + lane];
+          const double iRym = T[((size_t)8 * Ndyn + j) * N + lane];
+          const double in2 = fma(-B2, iRym, fma(-A2, iRxm, 1.0));
+          if (in2 > 0.0) {
+            const double ws = T[((size_t)9 * Ndyn + j) * N + lane];
+            soft = fma(in2 * in2, ws, soft);
+            if (GRAD) {
+              const double wg = ws * (2.0 * in2);
+              const double tA = A * iRxm, tB = B * iRym;
+              gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
+              gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);
+            }
           }
         }
       }
-      const bool hard = in1 > 0.0;
-      if (__any_sync(FULL, hard)) {
-        const double Dj = wsum(hard ? in1 : 0.0);
-        if (lane == 0) sm.D[j] = Dj;
-        if (j < 32) hard_mask_lo |= 1u << j; else hard_mask_hi |= 1u << (j - 32);
-      } else if (lane == 0) {
-        sm.D[j] = 0.0;
-      }
     }
     cost += soft;
-    bodies = __reduce_add_sync(FULL, bodies);
-    if (lane == 0) sm.ctx->n_body += bodies;
+    if (__any_sync(FULL, bodies != 0)) {
+      bodies = __reduce_add_sync(FULL, bodies);
+      if (lane == 0) sm.ctx->n_body += bodies;
+    }
+  }
+  // hard terms are rare: one vote for the whole loop, per-obstacle sums only when needed
+  const bool any_hard = __any_sync(FULL, hard_mask != 0);
+  unsigned long long warp_hard = 0;
+  if (any_hard) {
+    const unsigned lo = __reduce_or_sync(FULL, (unsigned)hard_mask);
+    const unsigned hi = __reduce_or_sync(FULL, (unsigned)(hard_mask >> 32));
+    warp_hard = ((unsigned long long)hi << 32) | lo;
+    const double *T = cx->dyn;
+#pragma unroll 1
+    for (int j = 0; j < Ndyn; j++) {
+      if (!(warp_hard >> j & 1ull)) { if (lane == 0) sm.D[j] = 0.0; continue; }
+      double in1 = 0.0;
+      if (hard_mask >> j & 1ull) {
+        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lane];
+        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lane];
+        const double ca_ = T[((size_t)3 * Ndyn + j) * N + lane];
+        const double sa_ = T[((size_t)4 * Ndyn + j) * N + lane];
+        const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
+        in1 = fma(-(B * B), T[((size_t)6 * Ndyn + j) * N + lane],
+                  fma(-(A * A), T[((size_t)5 * Ndyn + j) * N + lane], 1.0));
+      }
+      const double Dj = wsum(in1);
+      if (lane == 0) sm.D[j] = Dj;
+    }
+    __syncwarp();
   }
   // ---- terminal cost (l.242)
   double gt = 0.0;
@@ -394,9 +501,9 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   }
   // ---- static obstacles (l.214-220): hard penalty only
   if (act) {
-    const int ne = g.ne;
-    for (int i = 0; i < g.Nstc; i++) {
-      const double *b = sm.os + i * g.nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
+#pragma unroll 2
+    for (int i = 0; i < Nstc; i++) {
+      const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
       double m[MAX_EDGE], sq[MAX_EDGE];
       double inside = 1.0;
 #pragma unroll
@@ -432,28 +539,37 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   if (lane == 0) { vp = cx->v_init; wp = cx->w_init; }
   double aa = 0.0, aw = 0.0, ea = 0.0, ew = 0.0, alm = 0.0;
   if (act) {
-    aa = (v - vp) / ts; aw = (w - wp) / ts;
+    aa = (v - vp) * g.inv_ts; aw = (w - wp) * g.inv_ts;
     cost += fma(aw * aw, cx->wacc_pen, (aa * aa) * cx->acc_pen);
-    const double cm = fmax(c, 1.0);
-    double z = aa + ya / cm;
+    const double icm = 1.0 / fmax(c, 1.0);
+    double z = fma(ya, icm, aa);
     ea = z - clipd(z, g.amin, g.amax);
-    z = aw + yw / cm;
+    z = fma(yw, icm, aw);
     ew = z - clipd(z, -g.awmax, g.awmax);
     alm = fma(ew, ew, ea * ea);
   }
   // ---- reductions: f, ALM distance, static sum
   double f = cost, d2 = alm, S = S_loc;
   wsum3(f, d2, S);
-  __syncwarp();
   double f2sq = 0.0, sumF2 = 0.0;
-  for (int j = 0; j < g.Ndyn; j++) {
-    const double F2j = S + sm.D[j];
-    f2sq = fma(F2j, F2j, f2sq);
-    sumF2 += F2j;
+  if (any_hard) {
+#pragma unroll 1
+    for (int j = 0; j < Ndyn; j++) {
+      const double F2j = S + sm.D[j];
+      f2sq = fma(F2j, F2j, f2sq);
+      sumF2 += F2j;
+    }
+  } else {  // every D_j is zero: F2_j = S + 0.0 = S (same operations, no loads)
+#pragma unroll 1
+    for (int j = 0; j < Ndyn; j++) {
+      f2sq = fma(S, S, f2sq);
+      sumF2 += S;
+    }
   }
   EvalOut out;
   out.f = f; out.f2sq = f2sq; out.S = S;
   out.psi = f + c * d2 / 2 + c * f2sq / 2;
+  out.any_hard = any_hard;
 
   if (GRAD) {
     // hard-penalty gradient: c * sum_j F2_j * (grad S + grad D_j)
@@ -461,29 +577,23 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       const double cs_ = c * sumF2;
       gx = fma(cs_, gSx, gx);
       gy = fma(cs_, gSy, gy);
-      unsigned mlo = hard_mask_lo, mhi = hard_mask_hi;
-      const double *T = cx->dyn;
-      while (mlo | mhi) {
-        int j;
-        if (mlo) { j = __ffs(mlo) - 1; mlo &= mlo - 1; }
-        else     { j = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
-        if (act) {
-          const double ex = X - T[((size_t)0 * g.Ndyn + j) * N + lane];
-          const double ey = Y - T[((size_t)1 * g.Ndyn + j) * N + lane];
-          if (fma(ey, ey, ex * ex) < T[((size_t)2 * g.Ndyn + j) * N + lane]) {
-            const double ca_ = T[((size_t)3 * g.Ndyn + j) * N + lane];
-            const double sa_ = T[((size_t)4 * g.Ndyn + j) * N + lane];
-            const double iRx = T[((size_t)5 * g.Ndyn + j) * N + lane];
-            const double iRy = T[((size_t)6 * g.Ndyn + j) * N + lane];
-            const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
-            const double in1 = fma(-(B * B), iRy, fma(-(A * A), iRx, 1.0));
-            if (in1 > 0.0) {
-              const double wg = c * (S + sm.D[j]);
-              const double tA = A * iRx, tB = B * iRy;
-              gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
-              gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);
-            }
-          }
+      if (any_hard) {
+        unsigned long long mk = hard_mask;
+        const double *T = cx->dyn;
+        while (mk) {
+          const int j = __ffsll((long long)mk) - 1;
+          mk &= mk - 1;
+          const double ex = X - T[((size_t)0 * Ndyn + j) * N + lane];
+          const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lane];
+          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lane];
+          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lane];
+          const double iRx = T[((size_t)5 * Ndyn + j) * N + lane];
+          const double iRy = T[((size_t)6 * Ndyn + j) * N + lane];
+          const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
+          const double wg = c * (S + sm.D[j]);
+          const double tA = A * iRx, tB = B * iRy;
+          gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
+          gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);
         }
       }
     }
@@ -491,7 +601,12 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     const double dxdv = g.h6 * Cs, dydv = g.h6 * Ss;
     const double hvt = hv * ts;
     const double dxdw = -(hvt * fma(2.0, sb, sc)), dydw = hvt * fma(2.0, cb, cc);
-    const double lx = wsuffix(gx, lane), ly = wsuffix(gy, lane);
+    double lx = gx, ly = gy;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double ta = __shfl_down_sync(FULL, lx, o), tb = __shfl_down_sync(FULL, ly, o);
+      if (lane + o < 32) { lx += ta; ly += tb; }
+    }
     const double m = fma(ly, dx, -(lx * dy));
     const double lt = wsuffix(gt + m, lane) - m;
     // direct control terms
@@ -501,8 +616,8 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       const bool last = lane == N - 1;
       double dv = 2 * cx->qvel * (v - vr) + 2 * cx->rv * v;
       double dw = 2 * cx->rw * w;
-      dv += 2 * cx->acc_pen * (aa - (last ? 0.0 : aa_n)) / ts + c * (ea - (last ? 0.0 : ea_n)) / ts;
-      dw += 2 * cx->wacc_pen * (aw - (last ? 0.0 : aw_n)) / ts + c * (ew - (last ? 0.0 : ew_n)) / ts;
+      dv += (2 * cx->acc_pen * (aa - (last ? 0.0 : aa_n)) + c * (ea - (last ? 0.0 : ea_n))) * g.inv_ts;
+      dw += (2 * cx->wacc_pen * (aw - (last ? 0.0 : aw_n)) + c * (ew - (last ? 0.0 : ew_n))) * g.inv_ts;
       gv = dv + lx * dxdv + ly * dydv;
       gw = dw + lx * dxdw + ly * dydw + lt * ts;
     }

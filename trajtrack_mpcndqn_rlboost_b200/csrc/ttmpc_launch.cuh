@@ -13,7 +13,7 @@ struct SolveArgs {
   double *cost, *last_fpr, *f1_infeas, *f2_norm, *penalty;
   int *exit_status, *outer_iters, *inner_iters;
   double *pred_states;  // [n][N][3] or null
-  long long *evals;     // [n][2] or null
+  long long *evals;     // [n][4] or null
   double *dyn_scratch;  // [total_warps][DYN_FIELDS*Ndyn*N]
   int *work_counter;    // dynamic scene queue
   unsigned long long *stats;  // [4]: cost evals, grad evals, dyn bodies, panoc iterations
@@ -31,6 +31,8 @@ struct EvalArgs {
 cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st);
 cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream_t st);
 cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm);
+cudaError_t launch_probe(const DevCfg &g, const double *p, double *dyn, long long *out, int reps,
+                         cudaStream_t st);
 cudaError_t launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t st);
 
 }  // namespace ttmpc

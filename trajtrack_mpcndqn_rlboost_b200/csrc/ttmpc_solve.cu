@@ -96,6 +96,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   const int N = g.N;
   const bool act = lane < N;
   double q0 = z.d0, q1 = z.d1;
+#pragma unroll 1
   for (int i = 0; i < U.lb_active; i++) {
     const int k = lb_slot(g, U, i);
     const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
@@ -106,6 +107,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   }
   __syncwarp();
   q0 *= U.lb_gamma; q1 *= U.lb_gamma;
+#pragma unroll 1
   for (int i = U.lb_active - 1; i >= 0; i--) {
     const int k = lb_slot(g, U, i);
     const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
@@ -117,22 +119,30 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   z.d0 = q0; z.d1 = q1;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct Problem {  // what eval needs besides the point
   double c, ya, yw;
 };
 
+template <class DM>
 __device__ __forceinline__ double eval_cost(const DevCfg &g, const WarpSmem &sm, int lane,
                                             const Problem &pb, double a0, double a1) {
-  EvalOut e = eval_psi<false>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                              pb.yw, nullptr);
+  EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                           pb.yw, nullptr, false);
   if (lane == 0) sm.ctx->n_cost++;
   return e.psi;
 }
+template <class DM>
 __device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm, int lane,
                                             const Problem &pb, double a0, double a1, double &o0,
                                             double &o1) {
-  EvalOut e = eval_psi<true>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                             pb.yw, nullptr);
+  EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                           pb.yw, nullptr, true);
   if (lane == 0) sm.ctx->n_grad++;
   o0 = e.gv; o1 = e.gw;
   return e.psi;
@@ -149,6 +159,7 @@ __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z,
 }
 
 // PANOCEngine::step.  Returns true to continue.
+template <class DM>
 __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, int lane, const Problem &pb,
                            Lane &z, Uni &U, double tolerance) {
   if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
@@ -159,7 +170,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   }
   // update_lipschitz_constant
   {
-    double cost_half = eval_cost(g, sm, lane, pb, z.h0, z.h1);
+    double cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
     int it = 0;
     while (true) {
       const double ip = wsum(pdot(z.g0, z.g1, z.f0, z.f1));
@@ -172,7 +183,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       U.L *= 2.0;
       U.gamma /= 2.0;
       gradient_and_half_step(g, z, U, z.u0, z.u1);
-      cost_half = eval_cost(g, sm, lane, pb, z.h0, z.h1);
+      cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
       compute_fpr(z, U);
       it++;
     }
@@ -187,7 +198,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   if (U.iteration == 0) {
     // update_no_linesearch
     z.u0 = z.h0; z.u1 = z.h1;
-    U.cost = eval_grad(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
+    U.cost = eval_grad<DM>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
     gradient_and_half_step(g, z, U, z.u0, z.u1);
   } else {
     // linesearch on the forward-backward envelope
@@ -203,7 +214,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       const double one_m = 1.0 - U.tau;
       p0 = fma(-U.tau, z.d0, fma(-one_m, z.f0, z.u0));
       p1 = fma(-U.tau, z.d1, fma(-one_m, z.f1, z.u1));
-      U.cost = eval_grad(g, sm, lane, pb, p0, p1, z.g0, z.g1);
+      U.cost = eval_grad<DM>(g, sm, lane, pb, p0, p1, z.g0, z.g1);
       gradient_and_half_step(g, z, U, p0, p1);
       const double q0 = z.h0 - z.s0, q1 = z.h1 - z.s1;
       double dd = pdot(q0, q1, q0, q1), g2 = pdot(z.g0, z.g1, z.g0, z.g1), dm = 0.0;
@@ -225,10 +236,12 @@ __device__ __forceinline__ void panoc_reset(Uni &U) {
 }
 
 // One scene, start to finish.
+template <class DM>
 __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs &A, int scene,
                             int lane, unsigned long long *wstats) {
   const int N = g.N;
   const bool act = lane < N;
+  const unsigned long long t_start = globaltimer_ns();
   Lane z;
   Uni U;
   Problem pb;
@@ -267,7 +280,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     {
       panoc_reset(U);
       // init: cost, gradient, local Lipschitz estimate
-      U.cost = eval_grad(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
+      U.cost = eval_grad<DM>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
       if (lane == 0) sm.ctx->n_cost++;  // the reference evaluates cost and gradient separately
       {
         double h0 = 0.0, h1 = 0.0;
@@ -276,7 +289,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
           h1 = (EPSILON_LIPSCHITZ * z.u1 > DELTA_LIPSCHITZ) ? EPSILON_LIPSCHITZ * z.u1 : DELTA_LIPSCHITZ;
         }
         double t0, t1;
-        eval_grad(g, sm, lane, pb, z.u0 + h0, z.u1 + h1, t0, t1);
+        eval_grad<DM>(g, sm, lane, pb, z.u0 + h0, z.u1 + h1, t0, t1);
         const double e0 = t0 - z.g0, e1 = t1 - z.g1;
         double nh = pdot(h0, h1, h0, h1);
         double nd = pdot(e0, e1, e0, e1);
@@ -292,7 +305,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
       int num_iter = 0;
       bool cont = true;
       while (true) {
-        const bool flag = panoc_step(g, sm, lane, pb, z, U, g.tol);
+        const bool flag = panoc_step<DM>(g, sm, lane, pb, z, U, g.tol);
         if (!(flag && cont)) break;
         num_iter++;
         cont = num_iter < g.max_inner;
@@ -310,19 +323,19 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     {
       double vp = __shfl_up_sync(FULL, z.u0, 1), wp = __shfl_up_sync(FULL, z.u1, 1);
       if (lane == 0) { vp = sm.ctx->v_init; wp = sm.ctx->w_init; }
-      if (act) { F1a = (z.u0 - vp) / g.ts; F1w = (z.u1 - wp) / g.ts; }
+      if (act) { F1a = (z.u0 - vp) * g.inv_ts; F1w = (z.u1 - wp) * g.inv_ts; }
     }
     {
-      const double cm = fmax(pb.c, 1.0);
-      double t = clipd(F1a + pb.ya / cm, g.amin, g.amax);
+      const double icm = 1.0 / fmax(pb.c, 1.0);
+      double t = clipd(fma(pb.ya, icm, F1a), g.amin, g.amax);
       yp_a = pb.ya + pb.c * (F1a - t);
-      t = clipd(F1w + pb.yw / cm, -g.awmax, g.awmax);
+      t = clipd(fma(pb.yw, icm, F1w), -g.awmax, g.awmax);
       yp_w = pb.yw + pb.c * (F1w - t);
       if (!act) { yp_a = 0.0; yp_w = 0.0; }
     }
     {
-      EvalOut e = eval_psi<false>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0,
-                                  0.0, 0.0, nullptr);
+      EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0,
+                               0.0, nullptr, false);
       if (lane == 0) sm.ctx->n_cost++;
       f2_norm_plus = sqrt(e.f2sq);
       f_final = e.f;
@@ -360,8 +373,8 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     }
   }
   if (A.pred_states) {
-    eval_psi<false>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0, 0.0,
-                    A.pred_states + (size_t)scene * N * 3);
+    eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0, 0.0,
+                 A.pred_states + (size_t)scene * N * 3, false);
   }
   if (lane == 0) {
     if (A.cost) A.cost[scene] = f_final;
@@ -372,7 +385,11 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     if (A.f1_infeas) A.f1_infeas[scene] = delta_y_norm_plus / pb.c;
     if (A.f2_norm) A.f2_norm[scene] = f2_norm_plus;
     if (A.penalty) A.penalty[scene] = pb.c;
-    if (A.evals) { A.evals[2 * scene] = sm.ctx->n_cost; A.evals[2 * scene + 1] = sm.ctx->n_grad; }
+    if (A.evals) {
+      A.evals[4 * scene] = sm.ctx->n_cost; A.evals[4 * scene + 1] = sm.ctx->n_grad;
+      A.evals[4 * scene + 2] = (long long)(globaltimer_ns() - t_start);
+      A.evals[4 * scene + 3] = (long long)t_start;
+    }
     wstats[0] += sm.ctx->n_cost;
     wstats[1] += sm.ctx->n_grad;
     wstats[2] += sm.ctx->n_body;
@@ -380,7 +397,8 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
   }
 }
 
-__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevCfg g,
+template <class DM>
+__global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ DevCfg g,
                                                     const __grid_constant__ SolveArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevC
     scene = __shfl_sync(FULL, scene, 0);
     if (scene >= A.n_scenes) break;
     stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
-    solve_scene(g, sm, A, scene, lane, wstats);
+    solve_scene<DM>(g, sm, A, scene, lane, wstats);
     __syncwarp();
   }
   if (lane == 0 && A.stats) {
@@ -404,6 +422,7 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevC
 }
 
 // ------------------------------------------------------------------ batched evaluation
+template <class DM>
 __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevCfg g,
                                                    const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -423,24 +442,78 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevCf
       if (A.y) { ya = A.y[(size_t)scene * 2 * N + lane]; yw = A.y[(size_t)scene * 2 * N + N + lane]; }
     }
     const double c = A.c ? A.c[scene] : 0.0;
-    EvalOut e = eval_psi<true>(&g, reinterpret_cast<unsigned char *>(sm.ctx), v, w, c, ya, yw, nullptr);
+    EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), v, w, c, ya, yw, nullptr, true);
     const double gv = e.gv, gw = e.gw;
     double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
     if (lane == 0) { vp = sm.ctx->v_init; wp = sm.ctx->w_init; }
     if (act) {
       if (A.grad) { A.grad[(size_t)scene * 2 * N + 2 * lane] = gv; A.grad[(size_t)scene * 2 * N + 2 * lane + 1] = gw; }
       if (A.F1) {
-        A.F1[(size_t)scene * 2 * N + lane] = (v - vp) / g.ts;
-        A.F1[(size_t)scene * 2 * N + N + lane] = (w - wp) / g.ts;
+        A.F1[(size_t)scene * 2 * N + lane] = (v - vp) * g.inv_ts;
+        A.F1[(size_t)scene * 2 * N + N + lane] = (w - wp) * g.inv_ts;
       }
     }
     if (A.F2)
-      for (int j = lane; j < g.Ndyn; j += 32) A.F2[(size_t)scene * g.Ndyn + j] = e.S + sm.D[j];
+      for (int j = lane; j < g.Ndyn; j += 32)
+        A.F2[(size_t)scene * g.Ndyn + j] = e.S + (e.any_hard ? sm.D[j] : 0.0);
     if (lane == 0) {
       if (A.f) A.f[scene] = e.f;
       if (A.psi) A.psi[scene] = e.psi;
     }
     __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ latency probe (diagnostics)
+// One warp, one scene: cycles of a cost-only eval, a gradient eval, a butterfly sum, a
+// 10-pair L-BFGS apply and a double division, each averaged over `reps` back-to-back calls.
+template <class DM>
+__global__ void __launch_bounds__(128, 3) probe_kernel(const __grid_constant__ DevCfg g, const double *p,
+                                                       double *dyn, long long *out, int reps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) return;
+  const WarpSmem sm = carve(smem_raw, g);
+  stage_scene(g, sm, p, dyn, lane);
+  double v = lane < g.N ? 0.8 : 0.0, w = lane < g.N ? 0.05 : 0.0, acc = 0.0;
+  long long t0 = clock64();
+  for (int i = 0; i < reps; i++) {
+    EvalOut e = eval_psi<DM>(&g, smem_raw, v, w, 10.0, 0.0, 0.0, nullptr, false);
+    v += 1e-9 * e.psi * 0.0 + 1e-12;
+    acc += e.psi;
+  }
+  long long t1 = clock64();
+  for (int i = 0; i < reps; i++) {
+    EvalOut e = eval_psi<DM>(&g, smem_raw, v, w, 10.0, 0.0, 0.0, nullptr, true);
+    v += e.gv * 1e-300; w += e.gw * 1e-300;
+    acc += e.psi;
+  }
+  long long t2 = clock64();
+  for (int i = 0; i < reps; i++) acc = wsum(acc * 1e-3 + v);
+  long long t3 = clock64();
+  Lane z; Uni U;
+  z.d0 = v; z.d1 = w; U.lb_active = g.mem; U.lb_head = 0; U.lb_gamma = 0.7;
+  if (lane < g.N)
+    for (int k = 0; k <= g.mem; k++) {
+      sm.lbs[k * g.N + lane] = make_double2(0.01 * (k + 1), 0.02);
+      sm.lby[k * g.N + lane] = make_double2(0.03, 0.01 * (k + 2));
+    }
+  if (lane <= g.mem) sm.rho[lane] = 0.5;
+  __syncwarp();
+  for (int i = 0; i < reps; i++) { lbfgs_apply(g, sm, z, U, lane); z.d0 *= 1e-3; z.d1 *= 1e-3; }
+  long long t4 = clock64();
+  double d = 1.0 + acc * 1e-30;
+  for (int i = 0; i < reps; i++) d = 1.0 / (d + 0.5);
+  long long t5 = clock64();
+  for (int i = 0; i < reps; i++) d = sqrt(d + 0.5);
+  long long t6 = clock64();
+  double f = d;
+  for (int i = 0; i < reps; i++) f = fma(f, 0.999, 1e-3);
+  long long t7 = clock64();
+  if (lane == 0) {
+    out[0] = (t1 - t0) / reps; out[1] = (t2 - t1) / reps; out[2] = (t3 - t2) / reps;
+    out[3] = (t4 - t3) / reps; out[4] = (t5 - t4) / reps; out[5] = (t6 - t5) / reps;
+    out[6] = (t7 - t6) / reps; out[7] = (long long)(acc + z.d0 + d + f);
   }
 }
 
@@ -461,26 +534,63 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
 // ------------------------------------------------------------------ launch helpers (host)
 namespace ttmpc {
 
+static bool is_default_dims(const DevCfg &g) {
+  return g.N == 20 && g.Nother == 10 && g.Nstc == 10 && g.ne == 4 && g.Ndyn == 15;
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t smem) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st) {
   const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  solve_kernel<<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  cudaError_t e;
+  if (is_default_dims(g)) {
+    if ((e = set_smem(solve_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
+    solve_kernel<DimsDefault><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  } else {
+    if ((e = set_smem(solve_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
+    solve_kernel<DimsRuntime><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream_t st) {
   const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
-  cudaError_t e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  eval_kernel<<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  cudaError_t e;
+  if (is_default_dims(g)) {
+    if ((e = set_smem(eval_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
+    eval_kernel<DimsDefault><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  } else {
+    if ((e = set_smem(eval_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
+    eval_kernel<DimsRuntime><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  }
   return cudaGetLastError();
 }
 cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm) {
   const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel,
+  cudaError_t e;
+  if (is_default_dims(g)) {
+    if ((e = set_smem(solve_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<DimsDefault>,
+                                                         g.warps_per_block * 32, smem);
+  }
+  if ((e = set_smem(solve_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<DimsRuntime>,
                                                        g.warps_per_block * 32, smem);
+}
+cudaError_t launch_probe(const DevCfg &g, const double *p, double *dyn, long long *out, int reps,
+                         cudaStream_t st) {
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  cudaError_t e;
+  if (is_default_dims(g)) {
+    if ((e = set_smem(probe_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
+    probe_kernel<DimsDefault><<<1, 128, smem, st>>>(g, p, dyn, out, reps);
+  } else {
+    if ((e = set_smem(probe_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
+    probe_kernel<DimsRuntime><<<1, 128, smem, st>>>(g, p, dyn, out, reps);
+  }
+  return cudaGetLastError();
 }
 cudaError_t launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t st) {
   fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters);

@@ -58,7 +58,7 @@ class BatchSolution:
     penalty: object
     lagrange_multipliers: object  # [n, 2N], as left in the solver cache
     pred_states: object           # [n, N, 3]
-    evals: object                 # [n, 2]
+    evals: object                 # [n, 4]: cost evals, grad evals, solve ns, start ns
     solve_time_ms: float = 0.0
 
     def exit_status_names(self):
@@ -99,7 +99,7 @@ class BatchSolver:
             cost=np.zeros(n), exit_status=np.zeros(n, np.int32), outer=np.zeros(n, np.int32),
             inner=np.zeros(n, np.int32), fpr=np.zeros(n), f1=np.zeros(n), f2=np.zeros(n),
             pen=np.zeros(n), pred=np.zeros((n, N, 3)) if want_pred_states else None,
-            evals=np.zeros((n, 2), np.int64))
+            evals=np.zeros((n, 4), np.int64))
         res = TtmpcResult(u=_ptr(u), cost=_ptr(out["cost"]), exit_status=_ptr(out["exit_status"]),
                           outer_iters=_ptr(out["outer"]), inner_iters=_ptr(out["inner"]),
                           last_fpr=_ptr(out["fpr"]), f1_infeas=_ptr(out["f1"]), f2_norm=_ptr(out["f2"]),
@@ -129,7 +129,7 @@ class BatchSolver:
             outer=torch.zeros(n, **i32), inner=torch.zeros(n, **i32), fpr=torch.zeros(n, **f64),
             f1=torch.zeros(n, **f64), f2=torch.zeros(n, **f64), pen=torch.zeros(n, **f64),
             pred=torch.zeros(n, N, 3, **f64) if want_pred_states else None,
-            evals=torch.zeros(n, 2, dtype=torch.int64, device=device))
+            evals=torch.zeros(n, 4, dtype=torch.int64, device=device))
 
     def run_device(self, p, bufs: dict, use_u0: bool = False, use_y0: bool = False, c0=None,
                    stream=None) -> BatchSolution:
