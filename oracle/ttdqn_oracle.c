@@ -147,8 +147,9 @@ static float normalize_distance_f32(float d, float max_distance) {
 static void linear_f32(const float *w, const float *b, const float *x, int n_in, int n_out,
                        float *y, int relu) {
   for (int o = 0; o < n_out; o++) {
-    float acc = b[o];
-    for (int i = 0; i < n_in; i++) acc += w[o * n_in + i] * x[i];
+    double a = (double)b[o]; /* fp64 accumulation, one rounding to fp32 per neuron */
+    for (int i = 0; i < n_in; i++) a += (double)w[o * n_in + i] * (double)x[i];
+    float acc = (float)a;
     y[o] = (relu && acc < 0.0f) ? 0.0f : acc;
   }
 }

@@ -223,20 +223,23 @@ __global__ void __launch_bounds__(128) observe_act_kernel(const __grid_constant_
       for (int i = lane; i < n_ext; i += 32) A.ext[(size_t)env * n_ext + i] = x[i];
     if (have_net) {
       for (int o = lane; o < A.n_h1; o += 32) {
-        float acc = B0[o];
-        for (int i = 0; i < A.n_in; i++) acc += W0[o * A.n_in + i] * x[i];
+        double a = (double)B0[o];  // fp64 accumulation, one rounding to fp32 per neuron
+        for (int i = 0; i < A.n_in; i++) a += (double)W0[o * A.n_in + i] * (double)x[i];
+        const float acc = (float)a;
         h1[o] = acc < 0.0f ? 0.0f : acc;
       }
       __syncwarp();
       for (int o = lane; o < A.n_h2; o += 32) {
-        float acc = B1[o];
-        for (int i = 0; i < A.n_h1; i++) acc += W1[o * A.n_h1 + i] * h1[i];
+        double a = (double)B1[o];
+        for (int i = 0; i < A.n_h1; i++) a += (double)W1[o * A.n_h1 + i] * (double)h1[i];
+        const float acc = (float)a;
         h2[o] = acc < 0.0f ? 0.0f : acc;
       }
       __syncwarp();
       for (int o = lane; o < A.n_out; o += 32) {
-        float acc = B2[o];
-        for (int i = 0; i < A.n_h2; i++) acc += W2[o * A.n_h2 + i] * h2[i];
+        double a = (double)B2[o];
+        for (int i = 0; i < A.n_h2; i++) a += (double)W2[o * A.n_h2 + i] * (double)h2[i];
+        const float acc = (float)a;
         qv[o] = acc;
         if (A.q) A.q[(size_t)env * A.n_out + o] = acc;
       }
