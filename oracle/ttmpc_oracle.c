@@ -424,6 +424,8 @@ static void tt_sincos(double x, double *s, double *c) {
 }
 void ttmpc_oracle_sincos(double x, double *s, double *c) { tt_sincos(x, s, c); }
 
+static double relu_(double x) { return x > 0.0 ? x : 0.0; }
+static double clamp01_(double x) { const double t = x > 0.0 ? x : 0.0; return t < 1.0 ? t : 1.0; }
 #define WL 32
 static double w_sum(const double *v) { /* butterfly all-reduce, offsets 16..1 */
   double a[WL], b[WL];
@@ -544,16 +546,16 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
   double in1_all[MAXDYN][WL];
   for (int k = 0; k < N; k++) { /* per-lane work, lanes are independent here */
     /* reference path */
-    double dmin = 0.0; int jmin = k;
+    double dmin = INFINITY; int jmin = k;
     for (int j = k; j < N; j++) {
       const double s1x = W->seg[0][j], s1y = W->seg[1][j], sx = W->seg[2][j], sy = W->seg[3][j],
                    inv = W->seg[4][j];
       const double px = X[k] - s1x, py = Y[k] - s1y;
       const double t_hat = fma(py, sy, px * sx) * inv;
-      const double t = fmin(fmax(t_hat, 0.0), 1.0);
+      const double t = clamp01_(t_hat);
       const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
       const double d2 = fma(qy, qy, qx * qx);
-      if (j == k || !(dmin <= d2)) { dmin = d2; jmin = j; }
+      if (!(dmin <= d2)) { dmin = d2; jmin = j; }
     }
     cost[k] = dmin * qrpd;
     if (GRAD) {
@@ -562,7 +564,7 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
                    inv = W->seg[4][j];
       const double px = X[k] - s1x, py = Y[k] - s1y;
       const double t_hat = fma(py, sy, px * sx) * inv;
-      const double t = fmin(fmax(t_hat, 0.0), 1.0);
+      const double t = clamp01_(t_hat);
       const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
       const double pass = (t_hat >= 0.0 && t_hat <= 1.0) ? 1.0 : 0.0;
       const double cs = fma(qy, sy, qx * sx) * pass * inv;
@@ -639,7 +641,7 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
       double m[MAXEDGE], sq[MAXEDGE], inside = 1.0;
       for (int e = 0; e < ne; e++) {
         const double res = fma(na1[e], Y[k], fma(na0[e], X[k], b[e]));
-        m[e] = fmax(0.0, res);
+        m[e] = relu_(res);
         sq[e] = m[e] * m[e];
         inside *= sq[e];
       }
@@ -772,6 +774,7 @@ static void f_grad(prob_t *pb, const double *u, double *out) {
   else ttmpc_oracle_psi_grad(pb->g, u, pb->p, pb->c, pb->y, out);
   pb->n_grad++;
 }
+static int g_warp_mode = 0; /* set per solve; the vector helpers and L-BFGS read it */
 /* og.constraints.Rectangle(umin, umax) (mpc_generator.py:245-247) */
 static void project_u(const ttmpc_config *g, double *u) {
   for (int k = 0; k < g->N_hor; k++) {
@@ -780,7 +783,6 @@ static void project_u(const ttmpc_config *g, double *u) {
   }
 }
 
-static int g_warp_mode = 0; /* set per solve through prob_t; the vector helpers read it */
 static double dot(int n, const double *a, const double *b) {
   if (g_warp_mode) {
     double t[WL];
@@ -806,7 +808,17 @@ typedef struct {
   double s[MAXMEM + 1][MAXNU], y[MAXMEM + 1][MAXNU];
   double rho[MAXMEM + 1], alpha[MAXMEM];
   double old_state[MAXNU], old_g[MAXNU];
+  /* WARP order only: Gram matrices of the compact form (csrc/ttmpc_solve.cu) */
+  double gsy[MAXMEM + 1][MAXMEM + 1], gyy[MAXMEM + 1][MAXMEM + 1];
 } lbfgs_t;
+
+/* mirror of row_dot(): N steps of (x, y) pairs, four interleaved accumulators */
+static double row_dot(const double *a, const double *b, int N) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k = 0; k < N; k++)
+    acc[k & 3] = fma(a[2 * k + 1], b[2 * k + 1], fma(a[2 * k], b[2 * k], acc[k & 3]));
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
 
 static int lb_idx(const lbfgs_t *l, int i) { return (l->head + i) % (l->mem + 1); }
 static void lb_init(lbfgs_t *l, int n, int mem) {
@@ -816,8 +828,37 @@ static void lb_init(lbfgs_t *l, int n, int mem) {
   l->cbfgs_alpha = 1.0; l->cbfgs_eps = 1e-8; l->sy_eps = 1e-10;
 }
 static void lb_reset(lbfgs_t *l) { l->active = 0; l->first_old = 1; }
+/* compact (Gram) form of the same operator, operation order of the CUDA kernel */
+static void lb_apply_gram(lbfgs_t *l, double *q) {
+  const int m = l->active, N = l->n / 2;
+  double t[MAXMEM], w[MAXMEM], a[MAXMEM], cc[MAXMEM];
+  for (int i = 0; i < m; i++) {
+    t[i] = row_dot(l->s[lb_idx(l, i)], q, N);
+    w[i] = row_dot(l->y[lb_idx(l, i)], q, N);
+  }
+  for (int c = 0; c < m; c++) {
+    a[c] = l->rho[lb_idx(l, c)] * t[c];
+    for (int i = c + 1; i < m; i++) t[i] = fma(-a[c], l->gsy[lb_idx(l, i)][lb_idx(l, c)], t[i]);
+  }
+  for (int i = 0; i < m; i++) {
+    for (int c = 0; c < m; c++) w[i] = fma(-a[c], l->gyy[lb_idx(l, i)][lb_idx(l, c)], w[i]);
+    w[i] = l->gamma * w[i];
+  }
+  for (int c = m - 1; c >= 0; c--) {
+    cc[c] = a[c] - l->rho[lb_idx(l, c)] * w[c];
+    for (int i = 0; i < c; i++) w[i] = fma(cc[c], l->gsy[lb_idx(l, c)][lb_idx(l, i)], w[i]);
+  }
+  for (int e = 0; e < l->n; e++) {
+    double d = l->gamma * q[e];
+    for (int c = 0; c < m; c++) d = fma(-(l->gamma * a[c]), l->y[lb_idx(l, c)][e], d);
+    for (int c = m - 1; c >= 0; c--) d = fma(cc[c], l->s[lb_idx(l, c)][e], d);
+    q[e] = d;
+  }
+}
+
 static void lb_apply(lbfgs_t *l, double *q) {
   if (l->active == 0) return;
+  if (g_warp_mode) { lb_apply_gram(l, q); return; }
   const int n = l->n;
   for (int i = 0; i < l->active; i++) {
     int k = lb_idx(l, i);
@@ -864,6 +905,16 @@ static int lb_update(lbfgs_t *l, const double *g, const double *state, double no
   int k0 = lb_idx(l, 0);
   l->gamma = (1.0 / l->rho[k0]) / yy;
   l->active = (l->mem < l->active + 1) ? l->mem : l->active + 1;
+  if (g_warp_mode) { /* Gram row / column of the new pair */
+    const int N = n / 2;
+    l->gsy[k0][k0] = ys; l->gyy[k0][k0] = yy;
+    for (int i = 1; i < l->active; i++) {
+      int pl = lb_idx(l, i);
+      l->gsy[k0][pl] = row_dot(l->s[k0], l->y[pl], N);
+      l->gsy[pl][k0] = row_dot(l->s[pl], l->y[k0], N);
+      l->gyy[k0][pl] = l->gyy[pl][k0] = row_dot(l->y[k0], l->y[pl], N);
+    }
+  }
   return 1;
 }
 

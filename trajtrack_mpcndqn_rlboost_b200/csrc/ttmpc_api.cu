@@ -64,8 +64,9 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   if (c->N_hor < 1 || c->N_hor > 32) return fail(TTMPC_ERR_BAD_CONFIG, "N_hor must be in 1..32");
   if (c->nstcobs % 3 != 0 || c->nstcobs / 3 > MAX_EDGE || (c->Nstcobs > 0 && c->nstcobs < 3))
     return fail(TTMPC_ERR_BAD_CONFIG, "nstcobs must be 3*edges with edges <= 8");
-  if (c->Nother < 0 || c->Nstcobs < 0 || c->Ndynobs < 0 || c->Ndynobs > 64)
-    return fail(TTMPC_ERR_BAD_CONFIG, "obstacle counts out of range (Ndynobs <= 64)");
+  if (c->Nother < 0 || c->Nstcobs < 0 || c->Ndynobs < 0 || c->Ndynobs > 64 || c->Nother > 32 ||
+      c->Nstcobs > 32)
+    return fail(TTMPC_ERR_BAD_CONFIG, "obstacle counts out of range (Nother, Nstcobs <= 32, Ndynobs <= 64)");
   if (c->lbfgs_memory < 1 || c->lbfgs_memory > MAX_MEM)
     return fail(TTMPC_ERR_BAD_CONFIG, "lbfgs_memory must be in 1..16");
   if (c->max_inner_iterations < 1 || c->max_outer_iterations < 1 || !(c->ts > 0.0))

@@ -116,6 +116,13 @@ __device__ __forceinline__ double wsuffix(double v, int lane) {
 __device__ __forceinline__ double clipd(double z, double lo, double hi) {
   return fmin(fmax(z, lo), hi);
 }
+// max(0, x) and clamp to [0, 1] as compare+select (fmax/fmin semantics for every input,
+// NaN -> 0, but 3 instructions instead of 7 on the fp64 path)
+__device__ __forceinline__ double relu(double x) { return x > 0.0 ? x : 0.0; }
+__device__ __forceinline__ double clamp01(double x) {
+  const double t = x > 0.0 ? x : 0.0;
+  return t < 1.0 ? t : 1.0;
+}
 // per-lane share of an inner product of two lane-distributed vectors
 __device__ __forceinline__ double pdot(double a0, double a1, double b0, double b1) {
   return fma(a1, b1, a0 * b0);
@@ -131,20 +138,24 @@ struct WarpCtx {
   double qvel, rv, rw, qN, qthetaN, qrpd, acc_pen, wacc_pen;
   long long n_cost, n_grad, n_body;  // evaluation counters (lane 0 view)
   int nstc_active;                   // static obstacles that can ever be non-zero
+  float fleet_thr;                   // fp32 contact prefilter threshold (padded d^2)
 };
 
 struct WarpSmem {
   WarpCtx *ctx;
-  double *seg;    // [5][N]: s1x s1y sx sy inv_den
+  double *seg;    // [N][6]: s1x s1y | sx sy | inv_den pad  (three vector loads per segment)
   double *os;     // [Nstc*nstcobs] per obstacle: b[ne], -a0[ne], -a1[ne]
   double *D;      // [Ndyn] per-obstacle hard sums of the last evaluation
   double *vref;   // [N] speed reference
-  double2 *fleet; // [Nother][N] other robots' (x, y) at each step
-  float4 *dynb;   // [Ndyn][N] conservative fp32 bounding test: cx cy R2 -
-  double2 *lbs;   // [(mem+1)][N]
-  double2 *lby;   // [(mem+1)][N]
+  float2 *fleet;  // [Nother][N] other robots' (x, y), fp32 copy for the contact prefilter
+  float *dynb;    // [Ndyn][N][3] conservative fp32 bounding test: cx cy R2
+  double2 *lbs;   // [(mem+1)][NP]  L-BFGS s rows; NP = N|1 (odd stride: rows read by
+  double2 *lby;   // [(mem+1)][NP]  different lanes fall in different banks)
+  double2 *qrow;  // [NP]           vector the inverse Hessian is applied to
+  double *gsy;    // [(mem+1)][(mem+1)]  Gram matrix  s_p . y_q
+  double *gyy;    // [(mem+1)][(mem+1)]  Gram matrix  y_p . y_q
   double *rho;    // [mem+1]
-  double *alpha;  // [mem]
+  double *alpha;  // [2*(mem+1)]  gamma*a_c and (a_c - beta_c) of the last apply
 };
 
 // Compile-time problem dimensions (0 = take the value from DevCfg at run time).
@@ -164,15 +175,18 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, 
                                                    int mem) {
   size_t b = 0;
   b += (sizeof(WarpCtx) + 15) / 16 * 16;
-  b += sizeof(double) * 5 * N;
+  b += sizeof(double) * 6 * N;
   b += sizeof(double) * ((Nstc * nstcobs + 1) / 2 * 2);
   b += sizeof(double) * ((Ndyn + 1) / 2 * 2);
   b += sizeof(double) * ((N + 1) / 2 * 2);
-  b += sizeof(double2) * (size_t)Nother * N;
-  b += sizeof(float4) * (size_t)Ndyn * N;
-  b += sizeof(double2) * (size_t)(mem + 1) * N * 2;
+  b += (sizeof(float2) * (size_t)Nother * N + 15) / 16 * 16;
+  b += (sizeof(float) * 3 * (size_t)Ndyn * N + 15) / 16 * 16;
+  const int NP = N | 1;
+  b += sizeof(double2) * (size_t)(mem + 1) * NP * 2;
+  b += sizeof(double2) * (size_t)NP;
+  b += sizeof(double) * (size_t)(mem + 1) * (mem + 1) * 2;
   b += sizeof(double) * ((mem + 2) / 2 * 2);
-  b += sizeof(double) * ((mem + 1) / 2 * 2);
+  b += sizeof(double) * (2 * (mem + 1));
   return (int)((b + 15) / 16 * 16);
 }
 
@@ -180,14 +194,18 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
   WarpSmem w;
   unsigned char *q = base;
   w.ctx = reinterpret_cast<WarpCtx *>(q); q += (sizeof(WarpCtx) + 15) / 16 * 16;
-  w.lbs = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * g.N;
-  w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * g.N;
-  w.fleet = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.Nother * g.N;
-  w.dynb = reinterpret_cast<float4 *>(q); q += sizeof(float4) * (size_t)g.Ndyn * g.N;
-  w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 5 * g.N;
+  const int NP = g.N | 1;
+  w.lbs = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * NP;
+  w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * NP;
+  w.qrow = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)NP;
+  w.fleet = reinterpret_cast<float2 *>(q); q += (sizeof(float2) * (size_t)g.Nother * g.N + 15) / 16 * 16;
+  w.dynb = reinterpret_cast<float *>(q); q += (sizeof(float) * 3 * (size_t)g.Ndyn * g.N + 15) / 16 * 16;
+  w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 6 * g.N;
   w.os = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.Nstc * g.nstcobs + 1) / 2 * 2);
   w.D = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.Ndyn + 1) / 2 * 2);
   w.vref = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.N + 1) / 2 * 2);
+  w.gsy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(g.mem + 1) * (g.mem + 1);
+  w.gyy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(g.mem + 1) * (g.mem + 1);
   w.rho = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.mem + 2) / 2 * 2);
   w.alpha = reinterpret_cast<double *>(q);
   return w;
@@ -222,9 +240,9 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     double s1x = r[3 * j], s1y = r[3 * j + 1];
     double sx = r[3 * j2] - s1x, sy = r[3 * j2 + 1] - s1y;
     double den = fma(sy, sy, sx * sx) + 1e-16;
-    sm.seg[0 * g.N + j] = s1x; sm.seg[1 * g.N + j] = s1y;
-    sm.seg[2 * g.N + j] = sx;  sm.seg[3 * g.N + j] = sy;
-    sm.seg[4 * g.N + j] = 1.0 / den;
+    sm.seg[6 * j + 0] = s1x; sm.seg[6 * j + 1] = s1y;
+    sm.seg[6 * j + 2] = sx;  sm.seg[6 * j + 3] = sy;
+    sm.seg[6 * j + 4] = 1.0 / den; sm.seg[6 * j + 5] = 0.0;
   }
   // static half-spaces: keep b, store -a0 and -a1 (res = b + (-a0) x + (-a1) y).
   // An obstacle with an edge a0 = a1 = 0, b <= 0 (e.g. a zero-padded slot) has
@@ -257,7 +275,18 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
   // other robots: c is robot-major, (x y theta) per step (mpc_generator.py:207-209)
   const double *cpar = p + g.off_c;
   for (int t = lane; t < g.Nother * g.N; t += 32)
-    sm.fleet[t] = make_double2(cpar[(size_t)t * 3], cpar[(size_t)t * 3 + 1]);
+    sm.fleet[t] = make_float2((float)cpar[(size_t)t * 3], (float)cpar[(size_t)t * 3 + 1]);
+  if (lane == 0) {
+    // contact needs |p - o|^2 < d^2; the fp32 prefilter pads d by the worst rounding of the
+    // fp32 copies (8 ulp_f32 of the largest coordinate of this scene) so it never rejects a contact
+    double cmax = 0.0;
+    for (int t = 0; t < g.Nother * g.N; t++)
+      cmax = fmax(cmax, fmax(fabs(cpar[(size_t)t * 3]), fabs(cpar[(size_t)t * 3 + 1])));
+    const double d = sqrt(g.veh_d2), pad = 4.8e-7 * (2.0 * cmax + 2.0 * d + 1.0) + 1e-6;
+    float thr = __double2float_ru((d + pad) * (d + pad) * (1.0 + 1e-6));
+    if (!(cmax == cmax)) thr = INFINITY;  // NaN coordinates: let the exact test decide
+    c->fleet_thr = thr;
+  }
   // dynamic obstacle table
   const double *od = p + g.off_od, *qdyn = p + g.off_qdyn;
   const int npair = g.Ndyn * g.N;
@@ -288,7 +317,7 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
       const double rp = rmax + pad;
       float r2f = __double2float_ru(rp * rp * (1.0 + 1e-6));
       if (!(rmax == rmax) || !(cx == cx) || !(cy == cy)) r2f = 0.0f;  // NaN input: exact test is false too
-      sm.dynb[t] = make_float4((float)cx, (float)cy, r2f, 0.0f);
+      sm.dynb[3 * t] = (float)cx; sm.dynb[3 * t + 1] = (float)cy; sm.dynb[3 * t + 2] = r2f;
     }
   }
   __syncwarp();
@@ -301,27 +330,49 @@ struct EvalOut {
   double f2sq;  // |F2|^2
   double S;     // static hard sum (F2_j = S + D_j, D in smem when any_hard, else 0)
   double gv, gw;  // this lane's gradient entries (GRAD only)
+  // line-search fusion (GRAD and gamma_ls > 0): gradient step s = p - gamma*grad, half step
+  // h = proj(s), and the two reduced scalars of the forward-backward envelope
+  double s0, s1, h0, h1, dd, g2;
   bool any_hard;
 };
+
+struct D4 { double a, b, c, d; };
+static __device__ __noinline__ D4 wsum4v(double a, double b, double c, double d) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ta = __shfl_xor_sync(FULL, a, o), tb = __shfl_xor_sync(FULL, b, o);
+    const double tc = __shfl_xor_sync(FULL, c, o), td = __shfl_xor_sync(FULL, d, o);
+    a += ta; b += tb; c += tc; d += td;
+  }
+  D4 r; r.a = a; r.b = b; r.c = c; r.d = d;
+  return r;
+}
 
 // Evaluate psi (and its gradient when GRAD) at this lane's (v, w).
 // ya / yw are this lane's multipliers for the linear / angular acceleration rows.
 // DM carries the problem dimensions (compile-time for the default configuration).
 // GRAD is a run-time (warp-uniform) flag: one copy of the code serves both uses, which
 // keeps the hot loop inside the instruction cache.
+//
+// Lanes >= N carry v = w = 0, so their state equals lane N-1's; they run the same
+// instruction stream on lane N-1's table columns (no divergence regions) and their
+// contributions are zeroed before the reductions.  Rare events (fleet contact, inside a
+// static polygon, inside an ellipse's bounding circle) are entered through warp votes, so
+// the common path has no divergent branch at all.
 template <class DM>
-__device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_base, double v,
-                                         double w, double c, double ya, double yw,
-                                         double *st_out, const bool GRAD) {
+__device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_base, double v_in,
+                                         double w_in, double c, double ya, double yw,
+                                         double *st_out, const bool GRAD, const double gamma_ls) {
   const DevCfg &g = *gp;
   const WarpSmem sm = carve(smem_base, g);
   const int lane = threadIdx.x & 31;
-  double gv = 0.0, gw = 0.0;
+  const double v = lane < DM::N(g) ? v_in : 0.0, w = lane < DM::N(g) ? w_in : 0.0;
   const WarpCtx *cx = sm.ctx;
   const int N = DM::N(g), Nother = DM::Nother(g), Nstc = cx->nstc_active, ne = DM::ne(g),
             Ndyn = DM::Ndyn(g);
   const int nstcobs = 3 * ne;
   const bool act = lane < N;
+  const int lk = act ? lane : N - 1;  // table column this lane reads
   const double ts = g.ts;
 
   // ---- rollout (motion_model.py:153-176; RK4 of the unicycle = Simpson in theta):
@@ -352,99 +403,114 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   const double TH = cx->th0 + th_in;
   if (st_out && act) { st_out[3 * lane] = X; st_out[3 * lane + 1] = Y; st_out[3 * lane + 2] = TH; }
 
-  double cost = 0.0;         // this lane's share of f
+  double cost;               // this lane's share of f
   double gx = 0.0, gy = 0.0; // d psi / d position_{k+1}
   double S_loc = 0.0, gSx = 0.0, gSy = 0.0;
 
   // ---- reference-path deviation (l.124-139, 202): min over the remaining segments
   {
-    double dmin = 0.0; int jmin = lane;
+    double dmin = INFINITY; int jmin = lk;
+    const double2 *segv = reinterpret_cast<const double2 *>(sm.seg);
 #pragma unroll 5
     for (int j = 0; j < N; j++) {
-      const double s1x = sm.seg[j], s1y = sm.seg[N + j], sx = sm.seg[2 * N + j],
-                   sy = sm.seg[3 * N + j], inv = sm.seg[4 * N + j];
-      const double px = X - s1x, py = Y - s1y;
-      const double t_hat = fma(py, sy, px * sx) * inv;
-      const double t = fmin(fmax(t_hat, 0.0), 1.0);
-      const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
+      const double2 s1 = segv[3 * j], sd = segv[3 * j + 1];
+      const double inv = sm.seg[6 * j + 4];
+      const double px = X - s1.x, py = Y - s1.y;
+      const double t_hat = fma(py, sd.y, px * sd.x) * inv;
+      const double t = clamp01(t_hat);
+      const double qx = fma(t, sd.x, -px), qy = fma(t, sd.y, -py);
       const double d2 = fma(qy, qy, qx * qx);
-      if (j >= lane && (j == lane || !(dmin <= d2))) { dmin = d2; jmin = j; }
+      const bool take = (j >= lk) && !(dmin <= d2);  // first minimum wins ties
+      dmin = take ? d2 : dmin;
+      jmin = take ? j : jmin;
     }
-    if (act) {
-      cost = dmin * cx->qrpd;
-      if (GRAD) {
-        const int j = jmin;
-        const double s1x = sm.seg[j], s1y = sm.seg[N + j], sx = sm.seg[2 * N + j],
-                     sy = sm.seg[3 * N + j], inv = sm.seg[4 * N + j];
-        const double px = X - s1x, py = Y - s1y;
-        const double t_hat = fma(py, sy, px * sx) * inv;
-        const double t = fmin(fmax(t_hat, 0.0), 1.0);
-        const double qx = fma(t, sx, -px), qy = fma(t, sy, -py);
-        const double pass = (t_hat >= 0.0 && t_hat <= 1.0) ? 1.0 : 0.0;
-        const double cs = fma(qy, sy, qx * sx) * pass * inv;
-        gx = cx->qrpd * (2.0 * fma(cs, sx, -qx));
-        gy = cx->qrpd * (2.0 * fma(cs, sy, -qy));
-      }
+    cost = dmin * cx->qrpd;
+    if (GRAD) {
+      const int j = jmin;
+      const double2 s1 = segv[3 * j], sd = segv[3 * j + 1];
+      const double inv = sm.seg[6 * j + 4];
+      const double px = X - s1.x, py = Y - s1.y;
+      const double t_hat = fma(py, sd.y, px * sd.x) * inv;
+      const double t = clamp01(t_hat);
+      const double qx = fma(t, sd.x, -px), qy = fma(t, sd.y, -py);
+      const double pass = (t_hat >= 0.0 && t_hat <= 1.0) ? 1.0 : 0.0;
+      const double cs = fma(qy, sd.y, qx * sd.x) * pass * inv;
+      gx = cx->qrpd * (2.0 * fma(cs, sd.x, -qx));
+      gy = cx->qrpd * (2.0 * fma(cs, sd.y, -qy));
     }
   }
   // ---- speed reference + control action (l.203-204)
-  double vr = 0.0;
-  if (act) {
-    vr = sm.vref[lane];
+  const double vr = sm.vref[lk];
+  {
     const double dv_ = v - vr;
     cost += cx->qvel * (dv_ * dv_);
     cost += fma(cx->rw, w * w, cx->rv * (v * v));
   }
-  // ---- fleet collision (l.207-211)
-  if (act) {
-    double acc = 0.0, fx = 0.0, fy = 0.0;
+  // ---- fleet collision (l.207-211): contacts are rare -> fp32 prefilter from shared memory,
+  //      one vote, then the exact fp64 terms (parameters in global memory) for the flagged
+  //      robots in the same order (Nother <= 32)
+  const float Xf = (float)X, Yf = (float)Y;
+  {
+    unsigned hit = 0;
+    const float thr = cx->fleet_thr;
 #pragma unroll 5
     for (int j = 0; j < Nother; j++) {
-      const double2 o = sm.fleet[j * N + lane];
-      const double ex = X - o.x, ey = Y - o.y;
-      const double e = g.veh_d2 - fma(ey, ey, ex * ex);
-      if (e > 0.0) {
-        acc += e;
-        if (GRAD) { fx = fma(-2.0, ex, fx); fy = fma(-2.0, ey, fy); }
-      }
+      const float2 o = sm.fleet[j * N + lk];
+      const float exf = Xf - o.x, eyf = Yf - o.y;
+      hit |= (!((exf * exf + eyf * eyf) >= thr) ? 1u : 0u) << j;
     }
-    cost += 1000.0 * acc;
-    if (GRAD) { gx = fma(1000.0, fx, gx); gy = fma(1000.0, fy, gy); }
+    if (__any_sync(FULL, hit != 0)) {
+      const double *cp = cx->p + g.off_c + 3 * lk;
+      double acc = 0.0, fx = 0.0, fy = 0.0;
+      while (hit) {
+        const int j = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const double ex = X - cp[(size_t)j * 3 * N], ey = Y - cp[(size_t)j * 3 * N + 1];
+        const double e = g.veh_d2 - fma(ey, ey, ex * ex);
+        if (e > 0.0) {
+          acc += e;
+          if (GRAD) { fx = fma(-2.0, ex, fx); fy = fma(-2.0, ey, fy); }
+        }
+      }
+      cost += 1000.0 * acc;
+      if (GRAD) { gx = fma(1000.0, fx, gx); gy = fma(1000.0, fy, gy); }
+    }
   }
   // ---- dynamic obstacles (l.225-237): hard penalty D_j and soft cost.
   //      fp32 bounding test from shared memory first; the exact fp64 body (global
   //      table) only runs for pairs that can be non-zero.
   unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
   {
-    const double *T = cx->dyn;
-    const float Xf = (float)X, Yf = (float)Y;
-    double soft = 0.0;
-    int bodies = 0;
+    unsigned long long near_mask = 0;
 #pragma unroll 5
     for (int j = 0; j < Ndyn; j++) {
-      bool maybe = false;
-      if (act) {
-        const float4 b = sm.dynb[j * N + lane];
-        const float exf = Xf - b.x, eyf = Yf - b.y;
-        maybe = (exf * exf + eyf * eyf) < b.z;
-      }
-      if (maybe) {
-        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lane];
-        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lane];
-        if (fma(ey, ey, ex * ex) < T[((size_t)2 * Ndyn + j) * N + lane]) {
+      const float *b = sm.dynb + 3 * (j * N + lk);
+      const float exf = Xf - b[0], eyf = Yf - b[1];
+      near_mask |= (unsigned long long)((exf * exf + eyf * eyf) < b[2] ? 1u : 0u) << j;
+    }
+    if (__any_sync(FULL, near_mask != 0)) {
+      const double *T = cx->dyn;
+      double soft = 0.0;
+      int bodies = 0;
+      while (near_mask) {
+        const int j = __ffsll((long long)near_mask) - 1;
+        near_mask &= near_mask - 1;
+        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
+        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lk];
+        if (fma(ey, ey, ex * ex) < T[((size_t)2 * Ndyn + j) * N + lk]) {
           bodies++;
-          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lane];
-          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lane];
+          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lk];
+          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lk];
           const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
           const double A2 = A * A, B2 = B * B;
-          const double in1 = fma(-B2, T[((size_t)6 * Ndyn + j) * N + lane],
-                                 fma(-A2, T[((size_t)5 * Ndyn + j) * N + lane], 1.0));
+          const double in1 = fma(-B2, T[((size_t)6 * Ndyn + j) * N + lk],
+                                 fma(-A2, T[((size_t)5 * Ndyn + j) * N + lk], 1.0));
           if (in1 > 0.0) hard_mask |= 1ull << j;
-          const double iRxm = T[((size_t)7 * Ndyn + j) * N + lane];
-          const double iRym = T[((size_t)8 * Ndyn + j) * N + lane];
+          const double iRxm = T[((size_t)7 * Ndyn + j) * N + lk];
+          const double iRym = T[((size_t)8 * Ndyn + j) * N + lk];
           const double in2 = fma(-B2, iRym, fma(-A2, iRxm, 1.0));
           if (in2 > 0.0) {
-            const double ws = T[((size_t)9 * Ndyn + j) * N + lane];
+            const double ws = T[((size_t)9 * Ndyn + j) * N + lk];
             soft = fma(in2 * in2, ws, soft);
             if (GRAD) {
               const double wg = ws * (2.0 * in2);
@@ -455,33 +521,31 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
           }
         }
       }
-    }
-    cost += soft;
-    if (__any_sync(FULL, bodies != 0)) {
+      cost += soft;
+      if (!act) { bodies = 0; hard_mask = 0; }
       bodies = __reduce_add_sync(FULL, bodies);
       if (lane == 0) sm.ctx->n_body += bodies;
     }
   }
   // hard terms are rare: one vote for the whole loop, per-obstacle sums only when needed
   const bool any_hard = __any_sync(FULL, hard_mask != 0);
-  unsigned long long warp_hard = 0;
   if (any_hard) {
     const unsigned lo = __reduce_or_sync(FULL, (unsigned)hard_mask);
     const unsigned hi = __reduce_or_sync(FULL, (unsigned)(hard_mask >> 32));
-    warp_hard = ((unsigned long long)hi << 32) | lo;
+    const unsigned long long warp_hard = ((unsigned long long)hi << 32) | lo;
     const double *T = cx->dyn;
 #pragma unroll 1
     for (int j = 0; j < Ndyn; j++) {
       if (!(warp_hard >> j & 1ull)) { if (lane == 0) sm.D[j] = 0.0; continue; }
       double in1 = 0.0;
       if (hard_mask >> j & 1ull) {
-        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lane];
-        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lane];
-        const double ca_ = T[((size_t)3 * Ndyn + j) * N + lane];
-        const double sa_ = T[((size_t)4 * Ndyn + j) * N + lane];
+        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
+        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lk];
+        const double ca_ = T[((size_t)3 * Ndyn + j) * N + lk];
+        const double sa_ = T[((size_t)4 * Ndyn + j) * N + lk];
         const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
-        in1 = fma(-(B * B), T[((size_t)6 * Ndyn + j) * N + lane],
-                  fma(-(A * A), T[((size_t)5 * Ndyn + j) * N + lane], 1.0));
+        in1 = fma(-(B * B), T[((size_t)6 * Ndyn + j) * N + lk],
+                  fma(-(A * A), T[((size_t)5 * Ndyn + j) * N + lk], 1.0));
       }
       const double Dj = wsum(in1);
       if (lane == 0) sm.D[j] = Dj;
@@ -499,23 +563,38 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       gt = 2.0 * cx->qthetaN * dtg;
     }
   }
-  // ---- static obstacles (l.214-220): hard penalty only
-  if (act) {
+  // ---- static obstacles (l.214-220): hard penalty only.  Being inside a polygon is rare:
+  //      flag, one vote, second pass over the flagged obstacles in the same order.
+  {
+    unsigned in_mask = 0;  // Nstcobs <= 32
 #pragma unroll 2
     for (int i = 0; i < Nstc; i++) {
       const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
-      double m[MAX_EDGE], sq[MAX_EDGE];
       double inside = 1.0;
 #pragma unroll
       for (int e = 0; e < MAX_EDGE; e++) {
         if (e < ne) {
-          const double res = fma(na1[e], Y, fma(na0[e], X, b[e]));
-          m[e] = fmax(0.0, res);
-          sq[e] = m[e] * m[e];
-          inside *= sq[e];
+          const double m = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
+          inside *= m * m;
         }
       }
-      if (inside > 0.0) {
+      in_mask |= (inside > 0.0 ? 1u : 0u) << i;
+    }
+    if (__any_sync(FULL, in_mask != 0)) {
+      while (in_mask) {
+        const int i = __ffs(in_mask) - 1;
+        in_mask &= in_mask - 1;
+        const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
+        double m[MAX_EDGE], sq[MAX_EDGE];
+        double inside = 1.0;
+#pragma unroll
+        for (int e = 0; e < MAX_EDGE; e++) {
+          if (e < ne) {
+            m[e] = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
+            sq[e] = m[e] * m[e];
+            inside *= sq[e];
+          }
+        }
         S_loc += inside;
         if (GRAD) {
 #pragma unroll
@@ -537,9 +616,8 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   // ---- accelerations: cost (l.250-264) and the ALM set C = acc bounds
   double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
   if (lane == 0) { vp = cx->v_init; wp = cx->w_init; }
-  double aa = 0.0, aw = 0.0, ea = 0.0, ew = 0.0, alm = 0.0;
-  if (act) {
-    aa = (v - vp) * g.inv_ts; aw = (w - wp) * g.inv_ts;
+  double aa = (v - vp) * g.inv_ts, aw = (w - wp) * g.inv_ts, ea, ew, alm;
+  {
     cost += fma(aw * aw, cx->wacc_pen, (aa * aa) * cx->acc_pen);
     const double icm = 1.0 / fmax(c, 1.0);
     double z = fma(ya, icm, aa);
@@ -548,9 +626,14 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     ew = z - clipd(z, -g.awmax, g.awmax);
     alm = fma(ew, ew, ea * ea);
   }
-  // ---- reductions: f, ALM distance, static sum
-  double f = cost, d2 = alm, S = S_loc;
-  wsum3(f, d2, S);
+  // ---- lanes beyond the horizon contribute nothing
+  if (!act) {
+    cost = 0.0; gx = 0.0; gy = 0.0; S_loc = 0.0; gSx = 0.0; gSy = 0.0;
+    aa = 0.0; aw = 0.0; ea = 0.0; ew = 0.0; alm = 0.0;
+  }
+  // ---- static sum: needed before the gradient (weight c * sum F2); zero in most evaluations
+  double S = 0.0;
+  if (__any_sync(FULL, S_loc != 0.0)) S = wsum(S_loc);
   double f2sq = 0.0, sumF2 = 0.0;
   if (any_hard) {
 #pragma unroll 1
@@ -567,11 +650,13 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     }
   }
   EvalOut out;
-  out.f = f; out.f2sq = f2sq; out.S = S;
-  out.psi = f + c * d2 / 2 + c * f2sq / 2;
-  out.any_hard = any_hard;
+  out.f2sq = f2sq; out.S = S; out.any_hard = any_hard;
+  out.gv = 0.0; out.gw = 0.0;
+  out.s0 = out.s1 = out.h0 = out.h1 = out.dd = out.g2 = 0.0;
+  double ddp = 0.0, g2p = 0.0;
 
   if (GRAD) {
+    double gv = 0.0, gw = 0.0;
     // hard-penalty gradient: c * sum_j F2_j * (grad S + grad D_j)
     if (c != 0.0) {
       const double cs_ = c * sumF2;
@@ -583,12 +668,12 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
         while (mk) {
           const int j = __ffsll((long long)mk) - 1;
           mk &= mk - 1;
-          const double ex = X - T[((size_t)0 * Ndyn + j) * N + lane];
-          const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lane];
-          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lane];
-          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lane];
-          const double iRx = T[((size_t)5 * Ndyn + j) * N + lane];
-          const double iRy = T[((size_t)6 * Ndyn + j) * N + lane];
+          const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
+          const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lk];
+          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lk];
+          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lk];
+          const double iRx = T[((size_t)5 * Ndyn + j) * N + lk];
+          const double iRy = T[((size_t)6 * Ndyn + j) * N + lk];
           const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
           const double wg = c * (S + sm.D[j]);
           const double tA = A * iRx, tB = B * iRy;
@@ -621,8 +706,19 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       gv = dv + lx * dxdv + ly * dydv;
       gw = dw + lx * dxdw + ly * dydw + lt * ts;
     }
+    out.gv = gv; out.gw = gw;
+    if (gamma_ls > 0.0 && act) {  // PANOC line search: gradient step, projection, envelope terms
+      out.s0 = fma(-gamma_ls, gv, v); out.s1 = fma(-gamma_ls, gw, w);
+      out.h0 = clipd(out.s0, g.vmin, g.vmax); out.h1 = clipd(out.s1, -g.wmax, g.wmax);
+      const double q0 = out.h0 - out.s0, q1 = out.h1 - out.s1;
+      ddp = pdot(q0, q1, q0, q1);
+      g2p = pdot(gv, gw, gv, gw);
+    }
   }
-  out.gv = gv; out.gw = gw;
+  // ---- one batched reduction: f, ALM distance (and the line-search scalars)
+  const D4 r = wsum4v(cost, alm, ddp, g2p);
+  out.f = r.a; out.dd = r.c; out.g2 = r.d;
+  out.psi = r.a + c * r.b / 2 + c * f2sq / 2;
   return out;
 }
 

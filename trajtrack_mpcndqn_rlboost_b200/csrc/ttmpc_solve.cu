@@ -55,10 +55,39 @@ __device__ __forceinline__ int lb_slot(const DevCfg &g, const Uni &U, int i) {
   return s >= m1 ? s - m1 : s;
 }
 
+// ---------------------------------------------------------------- L-BFGS, Gram form
+// Same quasi-Newton operator as the lbfgs crate's two-loop recursion (same pairs, same
+// C-BFGS acceptance test, same H0 = gamma I), evaluated in its compact form: the two
+// loops only need the inner products s_i.q, y_i.q, s_i.y_l, y_i.y_l.  The Gram matrices
+// are kept up to date when a pair is accepted, the products with q are computed in ONE
+// "lane-per-dot" pass (lane j walks row j sequentially, no shuffles), and the two
+// triangular recurrences run with one lane per row.  20 dependent warp reductions per
+// apply become one pass + 2m broadcasts.  The CPU oracle mirrors this operation order.
+
+// dot product of two smem rows of N double2, four interleaved accumulators
+__device__ __forceinline__ double row_dot(const double2 *a, const double2 *b, int N) {
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  int k = 0;
+  for (; k + 3 < N; k += 4) {
+    const double2 a0 = a[k], b0 = b[k], a1 = a[k + 1], b1 = b[k + 1];
+    const double2 a2 = a[k + 2], b2 = b[k + 2], a3 = a[k + 3], b3 = b[k + 3];
+    acc0 = fma(a0.y, b0.y, fma(a0.x, b0.x, acc0));
+    acc1 = fma(a1.y, b1.y, fma(a1.x, b1.x, acc1));
+    acc2 = fma(a2.y, b2.y, fma(a2.x, b2.x, acc2));
+    acc3 = fma(a3.y, b3.y, fma(a3.x, b3.x, acc3));
+  }
+  for (; k < N; k++) {
+    const double2 av = a[k], bv = b[k];
+    const double t = fma(av.y, bv.y, fma(av.x, bv.x, (k & 3) == 0 ? acc0 : (k & 3) == 1 ? acc1 : (k & 3) == 2 ? acc2 : acc3));
+    if ((k & 3) == 0) acc0 = t; else if ((k & 3) == 1) acc1 = t; else if ((k & 3) == 2) acc2 = t; else acc3 = t;
+  }
+  return (acc0 + acc1) + (acc2 + acc3);
+}
+
 // lbfgs::update_hessian(g = fpr, state = u)
 __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm, Lane &z, Uni &U,
                                              int lane) {
-  const int N = g.N;
+  const int N = g.N, NP = g.N | 1, M1 = g.mem + 1;
   if (U.lb_first) {
     U.lb_first = 0;
     z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
@@ -77,44 +106,97 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
   }
   z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
   // rotate_right(1): scratch slot becomes slot 0
-  U.lb_head = U.lb_head + g.mem; if (U.lb_head >= g.mem + 1) U.lb_head -= g.mem + 1;
+  U.lb_head = U.lb_head + g.mem; if (U.lb_head >= M1) U.lb_head -= M1;
   const int k0 = U.lb_head;
   if (lane < N) {
-    sm.lbs[k0 * N + lane] = make_double2(sv0, sv1);
-    sm.lby[k0 * N + lane] = make_double2(yv0, yv1);
+    sm.lbs[k0 * NP + lane] = make_double2(sv0, sv1);
+    sm.lby[k0 * NP + lane] = make_double2(yv0, yv1);
   }
-  if (lane == 0) sm.rho[k0] = rho;
+  if (lane == 0) { sm.rho[k0] = rho; sm.gsy[k0 * M1 + k0] = ys; sm.gyy[k0 * M1 + k0] = yy; }
   U.lb_gamma = (1.0 / rho) / yy;
   U.lb_active = min(g.mem, U.lb_active + 1);
   __syncwarp();
-}
-
-// lbfgs::apply_hessian on the direction (two-loop recursion)
-__device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm, Lane &z,
-                                            const Uni &U, int lane) {
-  if (U.lb_active == 0) return;
-  const int N = g.N;
-  const bool act = lane < N;
-  double q0 = z.d0, q1 = z.d1;
-#pragma unroll 1
-  for (int i = 0; i < U.lb_active; i++) {
-    const int k = lb_slot(g, U, i);
-    const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
-    const double2 y = act ? sm.lby[k * N + lane] : make_double2(0.0, 0.0);
-    const double a = sm.rho[k] * wsum(pdot(s.x, s.y, q0, q1));
-    if (lane == 0) sm.alpha[i] = a;
-    q0 = fma(-a, y.x, q0); q1 = fma(-a, y.y, q1);
+  // Gram row / column of the new pair against the older active pairs: 3 products per pair
+  const int K = 3 * (U.lb_active - 1);
+  for (int base = 0; base < K; base += 32) {
+    const int j = base + lane;
+    if (j < K) {
+      const int l = 1 + j / 3, kind = j - 3 * (l - 1);
+      const int pl = lb_slot(g, U, l);
+      if (kind == 0)      sm.gsy[k0 * M1 + pl] = row_dot(sm.lbs + k0 * NP, sm.lby + pl * NP, N);
+      else if (kind == 1) sm.gsy[pl * M1 + k0] = row_dot(sm.lbs + pl * NP, sm.lby + k0 * NP, N);
+      else { const double v = row_dot(sm.lby + k0 * NP, sm.lby + pl * NP, N);
+             sm.gyy[k0 * M1 + pl] = v; sm.gyy[pl * M1 + k0] = v; }
+    }
   }
   __syncwarp();
-  q0 *= U.lb_gamma; q1 *= U.lb_gamma;
+}
+
+// lbfgs::apply_hessian on the direction, compact form (see above)
+__device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm, Lane &z,
+                                            const Uni &U, int lane) {
+  const int m = U.lb_active;
+  if (m == 0) return;
+  const int N = g.N, NP = g.N | 1, M1 = g.mem + 1;
+  const bool act = lane < N;
+  if (act) sm.qrow[lane] = make_double2(z.d0, z.d1);
+  __syncwarp();
+  // lane l < m: s_l . q      lane m + l: y_l . q      (2m <= 32)
+  double dotv = 0.0;
+  if (lane < 2 * m) {
+    const int l = lane < m ? lane : lane - m;
+    const int pl = lb_slot(g, U, l);
+    dotv = row_dot((lane < m ? sm.lbs : sm.lby) + pl * NP, sm.qrow, N);
+  }
+  const double yq = __shfl_sync(FULL, dotv, (lane + m) & 31);
+  const int pme = lb_slot(g, U, lane < m ? lane : 0);  // this lane's row (lanes < m)
+  const double rho_me = sm.rho[pme];
+  // forward recurrence: a_c = rho_c t_c ; t_l -= a_c (s_l . y_c) for l > c
+  double t = dotv, a_me = 0.0;
 #pragma unroll 1
-  for (int i = U.lb_active - 1; i >= 0; i--) {
-    const int k = lb_slot(g, U, i);
-    const double2 s = act ? sm.lbs[k * N + lane] : make_double2(0.0, 0.0);
-    const double2 y = act ? sm.lby[k * N + lane] : make_double2(0.0, 0.0);
-    const double beta = sm.rho[k] * wsum(pdot(y.x, y.y, q0, q1));
-    const double cf = sm.alpha[i] - beta;
-    q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
+  for (int c = 0; c < m; c++) {
+    const double a_c = __shfl_sync(FULL, rho_me * t, c);
+    if (lane == c) a_me = a_c;
+    if (lane > c && lane < m) t = fma(-a_c, sm.gsy[pme * M1 + lb_slot(g, U, c)], t);
+  }
+  // w_l = gamma (y_l . q - sum_c a_c (y_l . y_c)); the a_c go through shared memory so the
+  // loads pipeline and only the fma chain is serial
+  if (lane < m) sm.alpha[lane] = a_me;
+  __syncwarp();
+  double wv = yq;
+  if (lane < m) {
+#pragma unroll 4
+    for (int c = 0; c < m; c++) wv = fma(-sm.alpha[c], sm.gyy[pme * M1 + lb_slot(g, U, c)], wv);
+  }
+  wv = U.lb_gamma * wv;
+  __syncwarp();
+  // backward recurrence: beta_c = rho_c w_c ; cc_c = a_c - beta_c ; w_l += cc_c (s_c . y_l) for l < c
+  double cc_me = 0.0;
+#pragma unroll 1
+  for (int c = m - 1; c >= 0; c--) {
+    const double cc_c = __shfl_sync(FULL, a_me - rho_me * wv, c);
+    if (lane == c) cc_me = cc_c;
+    if (lane < c) wv = fma(cc_c, sm.gsy[lb_slot(g, U, c) * M1 + pme], wv);
+  }
+  if (lane < m) { sm.alpha[lane] = U.lb_gamma * a_me; sm.alpha[M1 + lane] = cc_me; }
+  __syncwarp();
+  // d = gamma q - sum_c (gamma a_c) y_c + sum_c cc_c s_c   (newest-to-oldest, then oldest-to-newest)
+  double q0 = U.lb_gamma * z.d0, q1 = U.lb_gamma * z.d1;
+  if (act) {
+#pragma unroll 2
+    for (int c = 0; c < m; c++) {
+      const double2 y = sm.lby[lb_slot(g, U, c) * NP + lane];
+      const double ga = sm.alpha[c];
+      q0 = fma(-ga, y.x, q0); q1 = fma(-ga, y.y, q1);
+    }
+#pragma unroll 2
+    for (int c = m - 1; c >= 0; c--) {
+      const double2 s = sm.lbs[lb_slot(g, U, c) * NP + lane];
+      const double cf = sm.alpha[M1 + c];
+      q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
+    }
+  } else {
+    q0 = 0.0; q1 = 0.0;
   }
   z.d0 = q0; z.d1 = q1;
 }
@@ -133,7 +215,7 @@ template <class DM>
 __device__ __forceinline__ double eval_cost(const DevCfg &g, const WarpSmem &sm, int lane,
                                             const Problem &pb, double a0, double a1) {
   EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                           pb.yw, nullptr, false);
+                           pb.yw, nullptr, false, 0.0);
   if (lane == 0) sm.ctx->n_cost++;
   return e.psi;
 }
@@ -142,7 +224,7 @@ __device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm,
                                             const Problem &pb, double a0, double a1, double &o0,
                                             double &o1) {
   EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                           pb.yw, nullptr, true);
+                           pb.yw, nullptr, true, 0.0);
   if (lane == 0) sm.ctx->n_grad++;
   o0 = e.gv; o1 = e.gw;
   return e.psi;
@@ -214,12 +296,13 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       const double one_m = 1.0 - U.tau;
       p0 = fma(-U.tau, z.d0, fma(-one_m, z.f0, z.u0));
       p1 = fma(-U.tau, z.d1, fma(-one_m, z.f1, z.u1));
-      U.cost = eval_grad<DM>(g, sm, lane, pb, p0, p1, z.g0, z.g1);
-      gradient_and_half_step(g, z, U, p0, p1);
-      const double q0 = z.h0 - z.s0, q1 = z.h1 - z.s1;
-      double dd = pdot(q0, q1, q0, q1), g2 = pdot(z.g0, z.g1, z.g0, z.g1), dm = 0.0;
-      wsum3(dd, g2, dm);
-      const double lhs_ls = U.cost - 0.5 * U.gamma * g2 + 0.5 * dd / U.gamma;
+      // cost, gradient, gradient step, half step and both envelope scalars in one evaluation
+      const EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), p0, p1, pb.c,
+                                     pb.ya, pb.yw, nullptr, true, U.gamma);
+      if (lane == 0) sm.ctx->n_grad++;
+      U.cost = e.psi;
+      z.g0 = e.gv; z.g1 = e.gw; z.s0 = e.s0; z.s1 = e.s1; z.h0 = e.h0; z.h1 = e.h1;
+      const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
       U.tau /= 2.0;
       nls++;
@@ -335,7 +418,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     }
     {
       EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0,
-                               0.0, nullptr, false);
+                               0.0, nullptr, false, 0.0);
       if (lane == 0) sm.ctx->n_cost++;
       f2_norm_plus = sqrt(e.f2sq);
       f_final = e.f;
@@ -374,7 +457,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
   }
   if (A.pred_states) {
     eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0, 0.0,
-                 A.pred_states + (size_t)scene * N * 3, false);
+                 A.pred_states + (size_t)scene * N * 3, false, 0.0);
   }
   if (lane == 0) {
     if (A.cost) A.cost[scene] = f_final;
@@ -442,7 +525,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevCf
       if (A.y) { ya = A.y[(size_t)scene * 2 * N + lane]; yw = A.y[(size_t)scene * 2 * N + N + lane]; }
     }
     const double c = A.c ? A.c[scene] : 0.0;
-    EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), v, w, c, ya, yw, nullptr, true);
+    EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), v, w, c, ya, yw, nullptr, true, 0.0);
     const double gv = e.gv, gw = e.gw;
     double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
     if (lane == 0) { vp = sm.ctx->v_init; wp = sm.ctx->w_init; }
@@ -478,13 +561,13 @@ __global__ void __launch_bounds__(128, 3) probe_kernel(const __grid_constant__ D
   double v = lane < g.N ? 0.8 : 0.0, w = lane < g.N ? 0.05 : 0.0, acc = 0.0;
   long long t0 = clock64();
   for (int i = 0; i < reps; i++) {
-    EvalOut e = eval_psi<DM>(&g, smem_raw, v, w, 10.0, 0.0, 0.0, nullptr, false);
+    EvalOut e = eval_psi<DM>(&g, smem_raw, v, w, 10.0, 0.0, 0.0, nullptr, false, 0.0);
     v += 1e-9 * e.psi * 0.0 + 1e-12;
     acc += e.psi;
   }
   long long t1 = clock64();
   for (int i = 0; i < reps; i++) {
-    EvalOut e = eval_psi<DM>(&g, smem_raw, v, w, 10.0, 0.0, 0.0, nullptr, true);
+    EvalOut e = eval_psi<DM>(&g, smem_raw, v, w, 10.0, 0.0, 0.0, nullptr, true, 1e-3);
     v += e.gv * 1e-300; w += e.gw * 1e-300;
     acc += e.psi;
   }
@@ -495,8 +578,8 @@ __global__ void __launch_bounds__(128, 3) probe_kernel(const __grid_constant__ D
   z.d0 = v; z.d1 = w; U.lb_active = g.mem; U.lb_head = 0; U.lb_gamma = 0.7;
   if (lane < g.N)
     for (int k = 0; k <= g.mem; k++) {
-      sm.lbs[k * g.N + lane] = make_double2(0.01 * (k + 1), 0.02);
-      sm.lby[k * g.N + lane] = make_double2(0.03, 0.01 * (k + 2));
+      sm.lbs[k * (g.N | 1) + lane] = make_double2(0.01 * (k + 1), 0.02);
+      sm.lby[k * (g.N | 1) + lane] = make_double2(0.03, 0.01 * (k + 2));
     }
   if (lane <= g.mem) sm.rho[lane] = 0.5;
   __syncwarp();
