@@ -6,8 +6,9 @@ import trajtrack_mpcndqn_rlboost_b200 as t
 name = sys.argv[1] if len(sys.argv) > 1 else "static4096"
 w = t.scenes.WORKLOADS[name]
 cfg = t.Configurator().to_ttmpc(**w["solver"])
+n_over = int(sys.argv[2]) if len(sys.argv) > 2 else w["n"]
 p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
-                         blocking_fraction=w["blocking_fraction"])
+                         blocking_fraction=w["blocking_fraction"])[:n_over]
 s = t.BatchSolver(cfg)
 dp = torch.from_numpy(p).cuda(); bufs = s.alloc_device(len(p))
 for _ in range(3):

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libttmpc.so")
+LIB_PATH = os.environ.get("TTMPC_LIB", os.path.join(_HERE, "libttmpc.so"))  # TTMPC_LIB: diagnostic builds
 
 
 class TtmpcConfig(C.Structure):

@@ -191,6 +191,16 @@ extern "C" int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes, c
 // Cumulative device-side counters since the last reset:
 // [0] cost-only evaluations [1] cost+gradient evaluations [2] dynamic-obstacle
 // bodies executed [3] PANOC iterations.  Synchronises the device.
+extern "C" int ttmpc_read_stats8(unsigned long long out[8], int reset) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace *w;
+  int rc = get_ws(&w);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, w->stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 64));
+  return TTMPC_OK;
+}
 extern "C" int ttmpc_read_stats(unsigned long long out[4], int reset) {
   std::lock_guard<std::mutex> lk(g_mu);
   Workspace *w;

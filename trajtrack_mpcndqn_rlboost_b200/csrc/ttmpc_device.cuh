@@ -113,15 +113,35 @@ __device__ __forceinline__ double wsuffix(double v, int lane) {
   }
   return v;
 }
-__device__ __forceinline__ double clipd(double z, double lo, double hi) {
+__device__ __forceinline__ double clipd_ref(double z, double lo, double hi) {
   return fmin(fmax(z, lo), hi);
 }
-// max(0, x) and clamp to [0, 1] as compare+select (fmax/fmin semantics for every input,
-// NaN -> 0, but 3 instructions instead of 7 on the fp64 path)
-__device__ __forceinline__ double relu(double x) { return x > 0.0 ? x : 0.0; }
+// Compare + select on doubles.  sm_100 has no DMNMX: fmax/fmin (and the C ternaries the
+// compiler canonicalises to them) expand to ~9 instructions each with NaN quieting.  A
+// setp/selp pair written in PTX stays 1 DSETP + 2 FSEL.  Semantics used below: the result is
+// `x` only when the comparison is TRUE, so NaN inputs fall to the constant, exactly like
+// fmax(x, 0) / fmin(., 1) do.
+__device__ __forceinline__ double sel_gt(double a, double b, double x, double y) {  // a > b ? x : y
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %3, %4, p;\n\t}"
+      : "=d"(r) : "d"(a), "d"(b), "d"(x), "d"(y));
+  return r;
+}
+__device__ __forceinline__ double sel_lt(double a, double b, double x, double y) {  // a < b ? x : y
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %3, %4, p;\n\t}"
+      : "=d"(r) : "d"(a), "d"(b), "d"(x), "d"(y));
+  return r;
+}
+// fmin(fmax(z, lo), hi) for every input (NaN -> lo), 6 instructions
+__device__ __forceinline__ double clipd(double z, double lo, double hi) {
+  const double t = sel_gt(z, lo, z, lo);
+  return sel_lt(t, hi, t, hi);
+}
+__device__ __forceinline__ double relu(double x) { return sel_gt(x, 0.0, x, 0.0); }
 __device__ __forceinline__ double clamp01(double x) {
-  const double t = x > 0.0 ? x : 0.0;
-  return t < 1.0 ? t : 1.0;
+  const double t = sel_gt(x, 0.0, x, 0.0);
+  return sel_lt(t, 1.0, t, 1.0);
 }
 // per-lane share of an inner product of two lane-distributed vectors
 __device__ __forceinline__ double pdot(double a0, double a1, double b0, double b1) {
@@ -139,6 +159,9 @@ struct WarpCtx {
   long long n_cost, n_grad, n_body;  // evaluation counters (lane 0 view)
   int nstc_active;                   // static obstacles that can ever be non-zero
   float fleet_thr;                   // fp32 contact prefilter threshold (padded d^2)
+#ifdef TTMPC_PROFILE
+  long long prof[8];                 // cycles per phase (diagnostic build only)
+#endif
 };
 
 struct WarpSmem {
@@ -160,8 +183,9 @@ struct WarpSmem {
 
 // Compile-time problem dimensions (0 = take the value from DevCfg at run time).
 // The default configuration (config/mpc_default.yaml) gets a fully specialised kernel.
-template <int N_, int NO_, int NS_, int NE_, int ND_>
+template <int N_, int NO_, int NS_, int NE_, int ND_, int MEM_ = 0>
 struct Dims {
+  __device__ __forceinline__ static int mem(const DevCfg &g) { return N_ ? MEM_ : g.mem; }
   __device__ __forceinline__ static int N(const DevCfg &g) { return N_ ? N_ : g.N; }
   __device__ __forceinline__ static int Nother(const DevCfg &g) { return N_ ? NO_ : g.Nother; }
   __device__ __forceinline__ static int Nstc(const DevCfg &g) { return N_ ? NS_ : g.Nstc; }
@@ -169,7 +193,7 @@ struct Dims {
   __device__ __forceinline__ static int Ndyn(const DevCfg &g) { return N_ ? ND_ : g.Ndyn; }
 };
 using DimsRuntime = Dims<0, 0, 0, 0, 0>;
-using DimsDefault = Dims<20, 10, 10, 4, 15>;
+using DimsDefault = Dims<20, 10, 10, 4, 15, 10>;
 
 __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, int nstcobs, int Ndyn,
                                                    int mem) {
@@ -232,6 +256,9 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     c->qvel = q[1]; c->rv = q[3]; c->rw = q[4]; c->qN = q[5]; c->qthetaN = q[6];
     c->qrpd = q[7]; c->acc_pen = q[8]; c->wacc_pen = q[9];
     c->n_cost = 0; c->n_grad = 0; c->n_body = 0;
+#ifdef TTMPC_PROFILE
+    for (int i = 0; i < 8; i++) c->prof[i] = 0;
+#endif
   }
   // reference-path segments: path_ref has N+1 points, last duplicated (l.190-191)
   const double *r = p + g.off_r;
@@ -411,7 +438,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   {
     double dmin = INFINITY; int jmin = lk;
     const double2 *segv = reinterpret_cast<const double2 *>(sm.seg);
-#pragma unroll 5
+#pragma unroll 2
     for (int j = 0; j < N; j++) {
       const double2 s1 = segv[3 * j], sd = segv[3 * j + 1];
       const double inv = sm.seg[6 * j + 4];
@@ -453,7 +480,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   {
     unsigned hit = 0;
     const float thr = cx->fleet_thr;
-#pragma unroll 5
+#pragma unroll 2
     for (int j = 0; j < Nother; j++) {
       const float2 o = sm.fleet[j * N + lk];
       const float exf = Xf - o.x, eyf = Yf - o.y;
@@ -482,7 +509,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
   {
     unsigned long long near_mask = 0;
-#pragma unroll 5
+#pragma unroll 3
     for (int j = 0; j < Ndyn; j++) {
       const float *b = sm.dynb + 3 * (j * N + lk);
       const float exf = Xf - b[0], eyf = Yf - b[1];
@@ -567,7 +594,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   //      flag, one vote, second pass over the flagged obstacles in the same order.
   {
     unsigned in_mask = 0;  // Nstcobs <= 32
-#pragma unroll 2
+#pragma unroll 1
     for (int i = 0; i < Nstc; i++) {
       const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
       double inside = 1.0;

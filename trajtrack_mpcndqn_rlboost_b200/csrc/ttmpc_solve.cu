@@ -41,6 +41,9 @@ struct Lane {
 
 struct Uni {  // warp-uniform scalars
   double gamma, L, sigma, cost, norm_fpr, tau, akkt_tol, lb_gamma;
+  double ip;              // <grad, fpr>, reduced together with |fpr|^2
+  double env_dd, env_g2;  // |gstep - u_half|^2 and |grad|^2 at the current iterate, as
+  int env_valid;          // returned by the accepted line-search evaluation
   int iteration, lb_active, lb_head, lb_first;
 };
 
@@ -49,9 +52,10 @@ __device__ __forceinline__ void project(const DevCfg &g, double a0, double a1, d
   o1 = clipd(a1, -g.wmax, g.wmax);
 }
 
+template <class DM>
 __device__ __forceinline__ int lb_slot(const DevCfg &g, const Uni &U, int i) {
   int s = U.lb_head + i;
-  const int m1 = g.mem + 1;
+  const int m1 = DM::mem(g) + 1;
   return s >= m1 ? s - m1 : s;
 }
 
@@ -65,7 +69,7 @@ __device__ __forceinline__ int lb_slot(const DevCfg &g, const Uni &U, int i) {
 // apply become one pass + 2m broadcasts.  The CPU oracle mirrors this operation order.
 
 // dot product of two smem rows of N double2, four interleaved accumulators
-__device__ __forceinline__ double row_dot(const double2 *a, const double2 *b, int N) {
+static __device__ __noinline__ double row_dot(const double2 *a, const double2 *b, int N) {
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
   int k = 0;
   for (; k + 3 < N; k += 4) {
@@ -85,9 +89,10 @@ __device__ __forceinline__ double row_dot(const double2 *a, const double2 *b, in
 }
 
 // lbfgs::update_hessian(g = fpr, state = u)
+template <class DM>
 __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm, Lane &z, Uni &U,
                                              int lane) {
-  const int N = g.N, NP = g.N | 1, M1 = g.mem + 1;
+  const int N = DM::N(g), NP = N | 1, MEM = DM::mem(g), M1 = MEM + 1;
   if (U.lb_first) {
     U.lb_first = 0;
     z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
@@ -106,7 +111,7 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
   }
   z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
   // rotate_right(1): scratch slot becomes slot 0
-  U.lb_head = U.lb_head + g.mem; if (U.lb_head >= M1) U.lb_head -= M1;
+  U.lb_head = U.lb_head + MEM; if (U.lb_head >= M1) U.lb_head -= M1;
   const int k0 = U.lb_head;
   if (lane < N) {
     sm.lbs[k0 * NP + lane] = make_double2(sv0, sv1);
@@ -114,7 +119,7 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
   }
   if (lane == 0) { sm.rho[k0] = rho; sm.gsy[k0 * M1 + k0] = ys; sm.gyy[k0 * M1 + k0] = yy; }
   U.lb_gamma = (1.0 / rho) / yy;
-  U.lb_active = min(g.mem, U.lb_active + 1);
+  U.lb_active = min(MEM, U.lb_active + 1);
   __syncwarp();
   // Gram row / column of the new pair against the older active pairs: 3 products per pair
   const int K = 3 * (U.lb_active - 1);
@@ -122,7 +127,7 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
     const int j = base + lane;
     if (j < K) {
       const int l = 1 + j / 3, kind = j - 3 * (l - 1);
-      const int pl = lb_slot(g, U, l);
+      const int pl = lb_slot<DM>(g, U, l);
       if (kind == 0)      sm.gsy[k0 * M1 + pl] = row_dot(sm.lbs + k0 * NP, sm.lby + pl * NP, N);
       else if (kind == 1) sm.gsy[pl * M1 + k0] = row_dot(sm.lbs + pl * NP, sm.lby + k0 * NP, N);
       else { const double v = row_dot(sm.lby + k0 * NP, sm.lby + pl * NP, N);
@@ -133,11 +138,12 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
 }
 
 // lbfgs::apply_hessian on the direction, compact form (see above)
+template <class DM>
 __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm, Lane &z,
                                             const Uni &U, int lane) {
   const int m = U.lb_active;
   if (m == 0) return;
-  const int N = g.N, NP = g.N | 1, M1 = g.mem + 1;
+  const int N = DM::N(g), NP = N | 1, M1 = DM::mem(g) + 1;
   const bool act = lane < N;
   if (act) sm.qrow[lane] = make_double2(z.d0, z.d1);
   __syncwarp();
@@ -145,11 +151,11 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   double dotv = 0.0;
   if (lane < 2 * m) {
     const int l = lane < m ? lane : lane - m;
-    const int pl = lb_slot(g, U, l);
+    const int pl = lb_slot<DM>(g, U, l);
     dotv = row_dot((lane < m ? sm.lbs : sm.lby) + pl * NP, sm.qrow, N);
   }
   const double yq = __shfl_sync(FULL, dotv, (lane + m) & 31);
-  const int pme = lb_slot(g, U, lane < m ? lane : 0);  // this lane's row (lanes < m)
+  const int pme = lb_slot<DM>(g, U, lane < m ? lane : 0);  // this lane's row (lanes < m)
   const double rho_me = sm.rho[pme];
   // forward recurrence: a_c = rho_c t_c ; t_l -= a_c (s_l . y_c) for l > c
   double t = dotv, a_me = 0.0;
@@ -157,7 +163,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   for (int c = 0; c < m; c++) {
     const double a_c = __shfl_sync(FULL, rho_me * t, c);
     if (lane == c) a_me = a_c;
-    if (lane > c && lane < m) t = fma(-a_c, sm.gsy[pme * M1 + lb_slot(g, U, c)], t);
+    if (lane > c && lane < m) t = fma(-a_c, sm.gsy[pme * M1 + lb_slot<DM>(g, U, c)], t);
   }
   // w_l = gamma (y_l . q - sum_c a_c (y_l . y_c)); the a_c go through shared memory so the
   // loads pipeline and only the fma chain is serial
@@ -166,7 +172,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   double wv = yq;
   if (lane < m) {
 #pragma unroll 4
-    for (int c = 0; c < m; c++) wv = fma(-sm.alpha[c], sm.gyy[pme * M1 + lb_slot(g, U, c)], wv);
+    for (int c = 0; c < m; c++) wv = fma(-sm.alpha[c], sm.gyy[pme * M1 + lb_slot<DM>(g, U, c)], wv);
   }
   wv = U.lb_gamma * wv;
   __syncwarp();
@@ -176,7 +182,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   for (int c = m - 1; c >= 0; c--) {
     const double cc_c = __shfl_sync(FULL, a_me - rho_me * wv, c);
     if (lane == c) cc_me = cc_c;
-    if (lane < c) wv = fma(cc_c, sm.gsy[lb_slot(g, U, c) * M1 + pme], wv);
+    if (lane < c) wv = fma(cc_c, sm.gsy[lb_slot<DM>(g, U, c) * M1 + pme], wv);
   }
   if (lane < m) { sm.alpha[lane] = U.lb_gamma * a_me; sm.alpha[M1 + lane] = cc_me; }
   __syncwarp();
@@ -185,13 +191,13 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   if (act) {
 #pragma unroll 2
     for (int c = 0; c < m; c++) {
-      const double2 y = sm.lby[lb_slot(g, U, c) * NP + lane];
+      const double2 y = sm.lby[lb_slot<DM>(g, U, c) * NP + lane];
       const double ga = sm.alpha[c];
       q0 = fma(-ga, y.x, q0); q1 = fma(-ga, y.y, q1);
     }
 #pragma unroll 2
     for (int c = m - 1; c >= 0; c--) {
-      const double2 s = sm.lbs[lb_slot(g, U, c) * NP + lane];
+      const double2 s = sm.lbs[lb_slot<DM>(g, U, c) * NP + lane];
       const double cf = sm.alpha[M1 + c];
       q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
     }
@@ -207,6 +213,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+#ifdef TTMPC_PROFILE
+#define PROF_BEGIN(v) const long long v = clock64();
+#define PROF_END(v, slot) if (lane == 0) sm.ctx->prof[slot] += clock64() - v;
+#else
+#define PROF_BEGIN(v)
+#define PROF_END(v, slot)
+#endif
+
 struct Problem {  // what eval needs besides the point
   double c, ya, yw;
 };
@@ -214,8 +228,19 @@ struct Problem {  // what eval needs besides the point
 template <class DM>
 __device__ __forceinline__ double eval_cost(const DevCfg &g, const WarpSmem &sm, int lane,
                                             const Problem &pb, double a0, double a1) {
+  PROF_BEGIN(t0)
   EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
                            pb.yw, nullptr, false, 0.0);
+  PROF_END(t0, 0)
+#ifdef TTMPC_PROFILE_DOUBLE
+  {  // I-cache experiment: the same evaluation again, timed separately (slot 4)
+    PROF_BEGIN(t1)
+    EvalOut e2 = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                              pb.yw, nullptr, false, 0.0);
+    PROF_END(t1, 4)
+    if (e2.psi != e.psi) __trap();
+  }
+#endif
   if (lane == 0) sm.ctx->n_cost++;
   return e.psi;
 }
@@ -223,16 +248,22 @@ template <class DM>
 __device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm, int lane,
                                             const Problem &pb, double a0, double a1, double &o0,
                                             double &o1) {
+  PROF_BEGIN(t0)
   EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
                            pb.yw, nullptr, true, 0.0);
+  PROF_END(t0, 1)
   if (lane == 0) sm.ctx->n_grad++;
   o0 = e.gv; o1 = e.gw;
   return e.psi;
 }
 
+// fixed point residual, its norm and <grad, fpr> in one batched reduction
 __device__ __forceinline__ void compute_fpr(Lane &z, Uni &U) {
   z.f0 = z.u0 - z.h0; z.f1 = z.u1 - z.h1;
-  U.norm_fpr = sqrt(wsum(pdot(z.f0, z.f1, z.f0, z.f1)));
+  double nf = pdot(z.f0, z.f1, z.f0, z.f1), ip = pdot(z.g0, z.g1, z.f0, z.f1), dm = 0.0;
+  wsum3(nf, ip, dm);
+  U.norm_fpr = sqrt(nf);
+  U.ip = ip;
 }
 __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z, const Uni &U,
                                                        double a0, double a1) {
@@ -255,13 +286,13 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
     double cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
     int it = 0;
     while (true) {
-      const double ip = wsum(pdot(z.g0, z.g1, z.f0, z.f1));
-      const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - ip +
+      const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
                          (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
       if (!(cost_half > rhs && it < MAX_LIPSCHITZ_UPDATE_ITERATIONS &&
             U.L < MAX_LIPSCHITZ_CONSTANT))
         break;
       U.lb_active = 0; U.lb_first = 1;  // lbfgs.reset()
+      U.env_valid = 0;                  // gamma changes: gradient step and half step move
       U.L *= 2.0;
       U.gamma /= 2.0;
       gradient_and_half_step(g, z, U, z.u0, z.u1);
@@ -272,21 +303,34 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
     U.sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * U.gamma);
   }
   // lbfgs_direction
-  lbfgs_update(g, sm, z, U, lane);
+  {
+    PROF_BEGIN(t0)
+    lbfgs_update<DM>(g, sm, z, U, lane);
+    PROF_END(t0, 2)
+  }
   if (U.iteration > 0) {
+    PROF_BEGIN(t0)
     z.d0 = z.f0; z.d1 = z.f1;
-    lbfgs_apply(g, sm, z, U, lane);
+    lbfgs_apply<DM>(g, sm, z, U, lane);
+    PROF_END(t0, 3)
   }
   if (U.iteration == 0) {
     // update_no_linesearch
     z.u0 = z.h0; z.u1 = z.h1;
     U.cost = eval_grad<DM>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
     gradient_and_half_step(g, z, U, z.u0, z.u1);
+    U.env_valid = 0;
   } else {
     // linesearch on the forward-backward envelope
-    const double e0 = z.s0 - z.h0, e1 = z.s1 - z.h1;
-    double dist2 = pdot(e0, e1, e0, e1), gg = pdot(z.g0, z.g1, z.g0, z.g1), dummy = 0.0;
-    wsum3(dist2, gg, dummy);
+    double dist2, gg;
+    if (U.env_valid) {  // same vectors as in the evaluation that produced this iterate
+      dist2 = U.env_dd; gg = U.env_g2;
+    } else {
+      const double e0 = z.s0 - z.h0, e1 = z.s1 - z.h1;
+      double dummy = 0.0;
+      dist2 = pdot(e0, e1, e0, e1); gg = pdot(z.g0, z.g1, z.g0, z.g1);
+      wsum3(dist2, gg, dummy);
+    }
     const double fbe = U.cost - 0.5 * U.gamma * gg + 0.5 * dist2 / U.gamma;
     const double rhs_ls = fbe - U.sigma * (U.norm_fpr * U.norm_fpr);
     U.tau = 1.0;
@@ -297,12 +341,15 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       p0 = fma(-U.tau, z.d0, fma(-one_m, z.f0, z.u0));
       p1 = fma(-U.tau, z.d1, fma(-one_m, z.f1, z.u1));
       // cost, gradient, gradient step, half step and both envelope scalars in one evaluation
+      PROF_BEGIN(t0)
       const EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), p0, p1, pb.c,
                                      pb.ya, pb.yw, nullptr, true, U.gamma);
+      PROF_END(t0, 1)
       if (lane == 0) sm.ctx->n_grad++;
       U.cost = e.psi;
       z.g0 = e.gv; z.g1 = e.gw; z.s0 = e.s0; z.s1 = e.s1; z.h0 = e.h0; z.h1 = e.h1;
       const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+      U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
       U.tau /= 2.0;
       nls++;
@@ -314,7 +361,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
 }
 
 __device__ __forceinline__ void panoc_reset(Uni &U) {
-  U.lb_active = 0; U.lb_first = 1;
+  U.lb_active = 0; U.lb_first = 1; U.env_valid = 0;
   U.tau = 1.0; U.L = 0.0; U.sigma = 0.0; U.cost = 0.0; U.iteration = 0; U.gamma = 0.0;
 }
 
@@ -325,6 +372,9 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
   const int N = g.N;
   const bool act = lane < N;
   const unsigned long long t_start = globaltimer_ns();
+#ifdef TTMPC_PROFILE
+  const long long t_clk0 = clock64();
+#endif
   Lane z;
   Uni U;
   Problem pb;
@@ -477,6 +527,15 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     wstats[1] += sm.ctx->n_grad;
     wstats[2] += sm.ctx->n_body;
     wstats[3] += panoc_iters;
+#ifdef TTMPC_PROFILE
+    // 4: cost evals, 5: grad evals, 6: lbfgs update + apply, 7: whole solve (cycles)
+    wstats[4] += sm.ctx->prof[0]; wstats[5] += sm.ctx->prof[1];
+#ifdef TTMPC_PROFILE_DOUBLE
+    wstats[5] = wstats[5] - sm.ctx->prof[1] + sm.ctx->prof[4];  // slot 5 := repeated cost evals
+#endif
+    wstats[6] += sm.ctx->prof[2] + sm.ctx->prof[3];
+    wstats[7] += clock64() - t_clk0;
+#endif
   }
 }
 
@@ -488,7 +547,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
   const WarpSmem sm = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
   const int gwarp = blockIdx.x * g.warps_per_block + warp;
   double *dyn = A.dyn_scratch + (size_t)gwarp * DYN_FIELDS * g.Ndyn * g.N;
-  unsigned long long wstats[4] = {0, 0, 0, 0};
+  unsigned long long wstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   while (true) {
     int scene = 0;
     if (lane == 0) scene = atomicAdd(A.work_counter, 1);
@@ -499,7 +558,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
     __syncwarp();
   }
   if (lane == 0 && A.stats) {
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 8; i++)
       if (wstats[i]) atomicAdd(A.stats + i, wstats[i]);
   }
 }
@@ -583,7 +642,7 @@ __global__ void __launch_bounds__(128, 3) probe_kernel(const __grid_constant__ D
     }
   if (lane <= g.mem) sm.rho[lane] = 0.5;
   __syncwarp();
-  for (int i = 0; i < reps; i++) { lbfgs_apply(g, sm, z, U, lane); z.d0 *= 1e-3; z.d1 *= 1e-3; }
+  for (int i = 0; i < reps; i++) { lbfgs_apply<DM>(g, sm, z, U, lane); z.d0 *= 1e-3; z.d1 *= 1e-3; }
   long long t4 = clock64();
   double d = 1.0 + acc * 1e-30;
   for (int i = 0; i < reps; i++) d = 1.0 / (d + 0.5);
@@ -618,7 +677,7 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
 namespace ttmpc {
 
 static bool is_default_dims(const DevCfg &g) {
-  return g.N == 20 && g.Nother == 10 && g.Nstc == 10 && g.ne == 4 && g.Ndyn == 15;
+  return g.N == 20 && g.Nother == 10 && g.Nstc == 10 && g.ne == 4 && g.Ndyn == 15 && g.mem == 10;
 }
 
 template <class K>
