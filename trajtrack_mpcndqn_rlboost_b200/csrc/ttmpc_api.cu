@@ -98,6 +98,10 @@ struct Workspace {
   int sm_count = 0;
   double *dyn_scratch = nullptr; size_t dyn_bytes = 0;
   int *work_counter = nullptr;
+  int *ready = nullptr;           // device counter of scenes already copied (host path)
+  int *h_ready = nullptr;         // pinned: one value per chunk
+  cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+  cudaEvent_t ev_inputs = nullptr;
   unsigned long long *stats = nullptr;
   // device staging for the host API
   void *dbuf = nullptr; size_t dbytes = 0;
@@ -117,6 +121,11 @@ static int get_ws(Workspace **out) {
   CUDA_TRY(cudaMalloc(&w.work_counter, 64));
   CUDA_TRY(cudaMalloc(&w.stats, 64));
   CUDA_TRY(cudaMemset(w.stats, 0, 64));
+  CUDA_TRY(cudaMalloc(&w.ready, 64));
+  CUDA_TRY(cudaHostAlloc(&w.h_ready, sizeof(int) * 4096, cudaHostAllocDefault));
+  CUDA_TRY(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&w.exec_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&w.ev_inputs, cudaEventDisableTiming));
   g_ws.reserve(16);
   g_ws.push_back(w);
   *out = &g_ws.back();
@@ -156,9 +165,19 @@ static int grid_for(Workspace *w, const DevCfg &g, int n_scenes, int *grid) {
   return TTMPC_OK;
 }
 
+static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double *d_p, int use_u0,
+                             int use_y0, const double *d_c0, const ttmpc_result *res,
+                             cudaStream_t st, const int *d_ready);
+
 extern "C" int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes, const double *d_p,
                                         int use_u0, int use_y0, const double *d_c0,
                                         const ttmpc_result *res, void *stream) {
+  return solve_device_impl(cfg, n_scenes, d_p, use_u0, use_y0, d_c0, res, (cudaStream_t)stream, nullptr);
+}
+
+static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double *d_p, int use_u0,
+                             int use_y0, const double *d_c0, const ttmpc_result *res,
+                             cudaStream_t st, const int *d_ready) {
   DevCfg g;
   int rc = make_devcfg(cfg, &g);
   if (rc) return rc;
@@ -175,9 +194,9 @@ extern "C" int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes, c
   const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
   rc = ensure_dyn(w, (table ? table : 8) * (size_t)grid * g.warps_per_block);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
   SolveArgs A;
+  A.ready = d_ready;
   A.p = d_p; A.c0 = d_c0; A.u = res->u; A.y = res->y; A.cost = res->cost;
   A.last_fpr = res->last_fpr; A.f1_infeas = res->f1_infeas; A.f2_norm = res->f2_norm;
   A.penalty = res->penalty; A.exit_status = res->exit_status; A.outer_iters = res->outer_iters;
@@ -286,29 +305,46 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   cv.take(nn, &dout, &hout);
   cv.take(nn, &din, &hin);
   cv.take(4 * nn, &dev, &hev);
-  cudaStream_t st = 0;
-  std::memcpy(hp, h_p, sizeof(double) * nn * g.np);
-  CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * nn * g.np, cudaMemcpyHostToDevice, st));
+  // Inputs stream in while the kernel already runs: small inputs first, then the parameter
+  // block in chunks (host memcpy into pinned staging -> async H2D -> bump the device-side
+  // `ready` counter); the persistent kernel waits on `ready` before it stages a scene.
+  cudaStream_t cs = w->copy_stream, st = w->exec_stream;
+  CUDA_TRY(cudaMemsetAsync(w->ready, 0, sizeof(int), cs));
   if (h_c0) {
     std::memcpy(hc0, h_c0, sizeof(double) * nn);
-    CUDA_TRY(cudaMemcpyAsync(dc0, hc0, sizeof(double) * nn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dc0, hc0, sizeof(double) * nn, cudaMemcpyHostToDevice, cs));
   }
   if (use_u0) {
     std::memcpy(hu, res->u, sizeof(double) * nn * nu);
-    CUDA_TRY(cudaMemcpyAsync(du, hu, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(du, hu, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, cs));
   }
   if (use_y0 && res->y) {
     std::memcpy(hy, res->y, sizeof(double) * nn * nu);
-    CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, cs));
   }
+  CUDA_TRY(cudaEventRecord(w->ev_inputs, cs));
+  CUDA_TRY(cudaStreamWaitEvent(st, w->ev_inputs, 0));
   ttmpc_result dres;
   std::memset(&dres, 0, sizeof(dres));
   dres.u = du; dres.y = res->y ? dy : nullptr; dres.cost = dcost; dres.exit_status = dex;
   dres.outer_iters = dout; dres.inner_iters = din; dres.last_fpr = dfpr; dres.f1_infeas = df1;
   dres.f2_norm = df2; dres.penalty = dpen; dres.pred_states = res->pred_states ? dps : nullptr;
   dres.evals = dev;
-  rc = ttmpc_solve_batch_device(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st);
+  rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w->ready);
   if (rc) return rc;
+  {
+    int chunk = 256;
+    while ((n + chunk - 1) / chunk > 4096) chunk *= 2;
+    int ci = 0;
+    for (int s0 = 0; s0 < n; s0 += chunk, ci++) {
+      const int s1 = s0 + chunk < n ? s0 + chunk : n;
+      const size_t off = (size_t)s0 * g.np, cnt = (size_t)(s1 - s0) * g.np;
+      std::memcpy(hp + off, h_p + off, sizeof(double) * cnt);
+      CUDA_TRY(cudaMemcpyAsync(dp + off, hp + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs));
+      w->h_ready[ci] = s1;
+      CUDA_TRY(cudaMemcpyAsync(w->ready, w->h_ready + ci, sizeof(int), cudaMemcpyHostToDevice, cs));
+    }
+  }
   // one contiguous D2H of everything after the inputs
   const size_t out_begin = (size_t)((char *)du - (char *)w->dbuf);
   CUDA_TRY(cudaMemcpyAsync((char *)w->hbuf + out_begin, (char *)w->dbuf + out_begin, cv.off - out_begin,

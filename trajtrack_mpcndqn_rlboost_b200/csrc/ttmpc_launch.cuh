@@ -16,6 +16,8 @@ struct SolveArgs {
   long long *evals;     // [n][4] or null
   double *dyn_scratch;  // [total_warps][DYN_FIELDS*Ndyn*N]
   int *work_counter;    // dynamic scene queue
+  const int *ready;     // optional: number of scenes whose parameters have landed in d_p
+                        // (host path streams p in chunks while the kernel already runs)
   unsigned long long *stats;  // [4]: cost evals, grad evals, dyn bodies, panoc iterations
   int n_scenes;
   int use_u0, use_y0;

@@ -553,6 +553,20 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
     if (lane == 0) scene = atomicAdd(A.work_counter, 1);
     scene = __shfl_sync(FULL, scene, 0);
     if (scene >= A.n_scenes) break;
+    if (A.ready) {  // parameters of this scene may still be on their way from the host
+      int ok = 1;
+      if (lane == 0) {
+        const volatile int *rdy = A.ready;
+        const unsigned long long t0 = globaltimer_ns();
+        while (*rdy <= scene) {
+          __nanosleep(200);
+          if (globaltimer_ns() - t0 > 4000000000ull) { ok = 0; break; }  // host died: never hang the GPU
+        }
+      }
+      ok = __shfl_sync(FULL, ok, 0);
+      if (!ok) break;
+      __threadfence();
+    }
     stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
     solve_scene<DM>(g, sm, A, scene, lane, wstats);
     __syncwarp();
