@@ -128,7 +128,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="static4096")
@@ -234,7 +234,10 @@ def main():
     local_ms = sum(kern_ms) / len(kern_ms)
     achieved = flops / (local_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                "frac": achieved / peak.value if peak.value else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch on this
+                # workload, ncu --set full capture profiles/r1_c_solve_kernel_final.txt
+                "traffic": 135.4e6 if args.workload == "static4096" else None,
                 "peak_source": "measured live: DFMA probe kernel (ttmpc_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "hbm_GBps_algorithmic": (p_host.nbytes + d2h) / (local_ms * 1e-3) / 1e9,

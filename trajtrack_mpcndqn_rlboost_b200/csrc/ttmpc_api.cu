@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -196,7 +197,7 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
   SolveArgs A;
-  A.ready = d_ready;
+  A.ready = d_ready; A.timeout_flag = d_ready ? w->ready + 1 : nullptr;
   A.p = d_p; A.c0 = d_c0; A.u = res->u; A.y = res->y; A.cost = res->cost;
   A.last_fpr = res->last_fpr; A.f1_infeas = res->f1_infeas; A.f2_norm = res->f2_norm;
   A.penalty = res->penalty; A.exit_status = res->exit_status; A.outer_iters = res->outer_iters;
@@ -309,7 +310,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   // block in chunks (host memcpy into pinned staging -> async H2D -> bump the device-side
   // `ready` counter); the persistent kernel waits on `ready` before it stages a scene.
   cudaStream_t cs = w->copy_stream, st = w->exec_stream;
-  CUDA_TRY(cudaMemsetAsync(w->ready, 0, sizeof(int), cs));
+  CUDA_TRY(cudaMemsetAsync(w->ready, 0, 2 * sizeof(int), cs));  // [0] ready count, [1] timeout flag
   if (h_c0) {
     std::memcpy(hc0, h_c0, sizeof(double) * nn);
     CUDA_TRY(cudaMemcpyAsync(dc0, hc0, sizeof(double) * nn, cudaMemcpyHostToDevice, cs));
@@ -330,8 +331,15 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   dres.outer_iters = dout; dres.inner_iters = din; dres.last_fpr = dfpr; dres.f1_infeas = df1;
   dres.f2_norm = df2; dres.penalty = dpen; dres.pred_states = res->pred_states ? dps : nullptr;
   dres.evals = dev;
-  rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w->ready);
-  if (rc) return rc;
+  // TTMPC_NO_STREAM=1 (or a profiler / CUDA_LAUNCH_BLOCKING that serialises launches) disables the
+  // overlap: everything is copied first, then the kernel is launched.
+  const char *ns = std::getenv("TTMPC_NO_STREAM");
+  const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING");
+  const bool stream_in = !(ns && ns[0] == '1') && !(lb && lb[0] == '1');
+  if (stream_in) {
+    rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w->ready);
+    if (rc) return rc;
+  }
   {
     int chunk = 256;
     while ((n + chunk - 1) / chunk > 4096) chunk *= 2;
@@ -344,6 +352,18 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
       w->h_ready[ci] = s1;
       CUDA_TRY(cudaMemcpyAsync(w->ready, w->h_ready + ci, sizeof(int), cudaMemcpyHostToDevice, cs));
     }
+  }
+  int timed_out = 0;
+  if (stream_in) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(&timed_out, w->ready + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (!stream_in || timed_out) {  // unstreamed (re-)run: all inputs are resident now
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    if (use_u0) CUDA_TRY(cudaMemcpyAsync(du, hu, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
+    if (use_y0 && res->y) CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
+    rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, nullptr);
+    if (rc) return rc;
   }
   // one contiguous D2H of everything after the inputs
   const size_t out_begin = (size_t)((char *)du - (char *)w->dbuf);

@@ -560,7 +560,9 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
         const unsigned long long t0 = globaltimer_ns();
         while (*rdy <= scene) {
           __nanosleep(200);
-          if (globaltimer_ns() - t0 > 4000000000ull) { ok = 0; break; }  // host died: never hang the GPU
+          if (globaltimer_ns() - t0 > 2000000000ull) {  // copies are not arriving: never hang the GPU
+            ok = 0; if (A.timeout_flag) atomicExch(A.timeout_flag, 1); break;
+          }
         }
       }
       ok = __shfl_sync(FULL, ok, 0);
