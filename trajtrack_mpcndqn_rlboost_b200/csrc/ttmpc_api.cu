@@ -196,7 +196,9 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   rc = ensure_dyn(w, (table ? table : 8) * (size_t)grid * g.warps_per_block);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
+  const char *nh = std::getenv("TTMPC_NO_HELPERS");
   SolveArgs A;
+  A.helpers = (nh && nh[0] == '1') ? 0 : 1;  // TTMPC_NO_HELPERS=1 disables the tail helpers
   A.ready = d_ready; A.timeout_flag = d_ready ? w->ready + 1 : nullptr;
   A.p = d_p; A.c0 = d_c0; A.u = res->u; A.y = res->y; A.cost = res->cost;
   A.last_fpr = res->last_fpr; A.f1_infeas = res->f1_infeas; A.f2_norm = res->f2_norm;

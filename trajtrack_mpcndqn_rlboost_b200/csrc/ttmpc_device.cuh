@@ -164,6 +164,7 @@ struct WarpCtx {
 #endif
 };
 
+struct HelpHdr;
 struct WarpSmem {
   WarpCtx *ctx;
   double *seg;    // [N][6]: s1x s1y | sx sy | inv_den pad  (three vector loads per segment)
@@ -179,6 +180,17 @@ struct WarpSmem {
   double *gyy;    // [(mem+1)][(mem+1)]  Gram matrix  y_p . y_q
   double *rho;    // [mem+1]
   double *alpha;  // [2*(mem+1)]  gamma*a_c and (a_c - beta_c) of the last apply
+  // mailbox of the tail helpers (see ttmpc_solve.cu): the owner's request / the helper's answer
+  double2 *hreq;  // [N] evaluation point (v, w)
+  double2 *hres;  // [N] gradient (gv, gw)
+  double2 *yrow;  // [N] the owner's current multipliers (ya, yw)
+  struct HelpHdr *hhdr;
+};
+struct HelpHdr {
+  int state;        // 0 idle, 1 request posted, 2 result ready
+  int grad;         // request: gradient wanted
+  double c, gamma_ls;
+  double psi, f, f2sq, S, dd, g2;  // result
 };
 
 // Compile-time problem dimensions (0 = take the value from DevCfg at run time).
@@ -211,6 +223,7 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, 
   b += sizeof(double) * (size_t)(mem + 1) * (mem + 1) * 2;
   b += sizeof(double) * ((mem + 2) / 2 * 2);
   b += sizeof(double) * (2 * (mem + 1));
+  b += sizeof(double2) * 3 * (size_t)N + 80;  // helper mailbox rows + header
   return (int)((b + 15) / 16 * 16);
 }
 
@@ -231,7 +244,11 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
   w.gsy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(g.mem + 1) * (g.mem + 1);
   w.gyy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(g.mem + 1) * (g.mem + 1);
   w.rho = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.mem + 2) / 2 * 2);
-  w.alpha = reinterpret_cast<double *>(q);
+  w.alpha = reinterpret_cast<double *>(q); q += sizeof(double) * (2 * (g.mem + 1));
+  w.hreq = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.N;
+  w.hres = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.N;
+  w.yrow = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.N;
+  w.hhdr = reinterpret_cast<HelpHdr *>(q);
   return w;
 }
 
@@ -389,9 +406,13 @@ static __device__ __noinline__ D4 wsum4v(double a, double b, double c, double d)
 template <class DM>
 __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_base, double v_in,
                                          double w_in, double c, double ya, double yw,
-                                         double *st_out, const bool GRAD, const double gamma_ls) {
+                                         double *st_out, const bool GRAD, const double gamma_ls,
+                                         double *Dalt = nullptr) {
+  // Dalt: a helper warp evaluating on another warp's scene tables brings its own scratch for
+  // the per-obstacle hard sums (and does not touch the owner's counters)
   const DevCfg &g = *gp;
   const WarpSmem sm = carve(smem_base, g);
+  double *const Dv = Dalt ? Dalt : sm.D;
   const int lane = threadIdx.x & 31;
   const double v = lane < DM::N(g) ? v_in : 0.0, w = lane < DM::N(g) ? w_in : 0.0;
   const WarpCtx *cx = sm.ctx;
@@ -551,7 +572,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       cost += soft;
       if (!act) { bodies = 0; hard_mask = 0; }
       bodies = __reduce_add_sync(FULL, bodies);
-      if (lane == 0) sm.ctx->n_body += bodies;
+      if (lane == 0 && !Dalt) sm.ctx->n_body += bodies;
     }
   }
   // hard terms are rare: one vote for the whole loop, per-obstacle sums only when needed
@@ -563,7 +584,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     const double *T = cx->dyn;
 #pragma unroll 1
     for (int j = 0; j < Ndyn; j++) {
-      if (!(warp_hard >> j & 1ull)) { if (lane == 0) sm.D[j] = 0.0; continue; }
+      if (!(warp_hard >> j & 1ull)) { if (lane == 0) Dv[j] = 0.0; continue; }
       double in1 = 0.0;
       if (hard_mask >> j & 1ull) {
         const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
@@ -575,7 +596,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
                   fma(-(A * A), T[((size_t)5 * Ndyn + j) * N + lk], 1.0));
       }
       const double Dj = wsum(in1);
-      if (lane == 0) sm.D[j] = Dj;
+      if (lane == 0) Dv[j] = Dj;
     }
     __syncwarp();
   }
@@ -665,7 +686,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   if (any_hard) {
 #pragma unroll 1
     for (int j = 0; j < Ndyn; j++) {
-      const double F2j = S + sm.D[j];
+      const double F2j = S + Dv[j];
       f2sq = fma(F2j, F2j, f2sq);
       sumF2 += F2j;
     }
@@ -702,7 +723,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
           const double iRx = T[((size_t)5 * Ndyn + j) * N + lk];
           const double iRy = T[((size_t)6 * Ndyn + j) * N + lk];
           const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
-          const double wg = c * (S + sm.D[j]);
+          const double wg = c * (S + Dv[j]);
           const double tA = A * iRx, tB = B * iRy;
           gx = fma(wg, -2.0 * fma(tB, sa_, tA * ca_), gx);
           gy = fma(wg, -2.0 * fma(-tB, ca_, tA * sa_), gy);

@@ -271,19 +271,186 @@ __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z,
   project(g, z.s0, z.s1, z.h0, z.h1);
 }
 
+// ---------------------------------------------------------------- tail helpers
+// When the scene queue is empty, warps without work help the CTA-mates that still own a
+// long-running scene: the owner posts evaluation points into a mailbox, the helper evaluates
+// them on the owner's shared-memory tables.  The owner uses this to (a) overlap the Lipschitz
+// check psi(u_half) with the L-BFGS update/apply and (b) evaluate the next line-search
+// candidate speculatively.  Results never depend on whether a helper was there: speculative
+// work is discarded when the sequential algorithm would not have asked for it.
+struct CtaHelp {
+  int busy[8];    // warp w owns a live scene (tables staged)
+  int helper[8];  // helper[m] = warp helping owner m, or -1
+};
+struct HelpCtl {
+  bool enabled;              // helpers exist in this launch and have not timed out on this scene
+  volatile int *slot;        // &cta->helper[me]
+  bool pending;              // a posted request has not been collected yet
+};
+
+__device__ __forceinline__ bool help_available(const HelpCtl &hc) {
+  return hc.enabled && *hc.slot >= 0;
+}
+__device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int lane, int N, EvalOut &e);
+// The mailbox lives in the owner's shared-memory region (request row, answer row, header).
+__device__ __forceinline__ void help_post(HelpCtl &hc, const WarpSmem &sm, int lane, int N, double v,
+                                          double w, double c, int grad, double gamma_ls) {
+  if (hc.pending) {  // a speculative evaluation nobody needed: let it finish first
+    EvalOut tmp;
+    if (!help_wait(hc, sm, lane, N, tmp)) return;
+  }
+  if (lane < N) sm.hreq[lane] = make_double2(v, w);
+  if (lane == 0) { sm.hhdr->c = c; sm.hhdr->gamma_ls = gamma_ls; sm.hhdr->grad = grad; }
+  __threadfence_block();
+  __syncwarp();
+  if (lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 1;
+  hc.pending = true;
+}
+// Collect the posted evaluation.  false = the helper did not answer in time (treated as gone).
+__device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int lane, int N, EvalOut &e) {
+  int ok = 1;
+  if (lane == 0) {
+    const volatile int *st = reinterpret_cast<volatile int *>(&sm.hhdr->state);
+    const unsigned long long t0 = globaltimer_ns();
+    int spins = 0;
+    while (*st != 2) {
+      if (((++spins) & 1023) == 0 && globaltimer_ns() - t0 > 50000000ull) { ok = 0; break; }
+    }
+  }
+  ok = __shfl_sync(FULL, ok, 0);
+  hc.pending = false;
+  if (!ok) { hc.enabled = false; return false; }
+  __threadfence_block();
+  const volatile HelpHdr *h = sm.hhdr;
+  e.psi = h->psi; e.f = h->f; e.f2sq = h->f2sq; e.S = h->S; e.dd = h->dd; e.g2 = h->g2;
+  {
+    const volatile double *hr = reinterpret_cast<const volatile double *>(sm.hres);
+    e.gv = lane < N ? hr[2 * lane] : 0.0;
+    e.gw = lane < N ? hr[2 * lane + 1] : 0.0;
+  }
+  e.any_hard = false;
+  e.s0 = e.s1 = e.h0 = e.h1 = 0.0;
+  __syncwarp();
+  if (lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 0;
+  return true;
+}
+__device__ __forceinline__ void help_drain(HelpCtl &hc, const WarpSmem &sm, int lane, int N) {
+  if (hc.pending) { EvalOut tmp; help_wait(hc, sm, lane, N, tmp); }
+}
+
+// A warp that ran out of scenes serves its CTA-mates until none of them owns a scene.
+template <class DM>
+__device__ void helper_loop(const DevCfg &g, const SolveArgs &A, CtaHelp *cta, unsigned char *smem_raw,
+                            int warp, int lane) {
+  const int W = g.warps_per_block;
+  const WarpSmem mine = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
+  unsigned long long t_idle = globaltimer_ns();
+  while (true) {
+    int m = -1, any_busy = 0;
+    if (lane == 0) {
+      for (int k = 1; k < W; k++) {
+        const int cand = (warp + k) % W;
+        if (*reinterpret_cast<volatile int *>(&cta->busy[cand])) {
+          any_busy = 1;
+          if (atomicCAS(&cta->helper[cand], -1, warp) == -1) { m = cand; break; }
+        }
+      }
+    }
+    m = __shfl_sync(FULL, m, 0);
+    any_busy = __shfl_sync(FULL, any_busy, 0);
+    if (m < 0) {
+      if (!any_busy || globaltimer_ns() - t_idle > 3000000000ull) return;
+      __nanosleep(2000);
+      continue;
+    }
+    unsigned char *base_m = smem_raw + (size_t)m * g.smem_per_warp;
+    const WarpSmem own = carve(base_m, g);
+    const int N = g.N;
+    while (true) {
+      int st = 0, alive = 1;
+      if (lane == 0) {
+        st = *reinterpret_cast<volatile int *>(&own.hhdr->state);
+        alive = *reinterpret_cast<volatile int *>(&cta->busy[m]);
+      }
+      st = __shfl_sync(FULL, st, 0);
+      alive = __shfl_sync(FULL, alive, 0);
+      if (st == 1) {
+        __threadfence_block();
+        const volatile HelpHdr *h = own.hhdr;
+        double2 pt = make_double2(0.0, 0.0), yv = make_double2(0.0, 0.0);
+        if (lane < N) {
+          const volatile double *rq = reinterpret_cast<const volatile double *>(own.hreq);
+          const volatile double *yr = reinterpret_cast<const volatile double *>(own.yrow);
+          pt.x = rq[2 * lane]; pt.y = rq[2 * lane + 1];
+          yv.x = yr[2 * lane]; yv.y = yr[2 * lane + 1];
+        }
+        const double c = h->c, gamma_ls = h->gamma_ls;
+        const int grad = h->grad;
+        const EvalOut e = eval_psi<DM>(&g, base_m, pt.x, pt.y, c, yv.x, yv.y, nullptr, grad != 0, gamma_ls, mine.D);
+        if (lane < N) own.hres[lane] = make_double2(e.gv, e.gw);
+        if (lane == 0) {
+          own.hhdr->psi = e.psi; own.hhdr->f = e.f; own.hhdr->f2sq = e.f2sq; own.hhdr->S = e.S;
+          own.hhdr->dd = e.dd; own.hhdr->g2 = e.g2;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int *>(&own.hhdr->state) = 2;
+        t_idle = globaltimer_ns();
+      } else if (!alive) {
+        if (lane == 0) atomicExch(&cta->helper[m], -1);
+        break;
+      } else {
+        __nanosleep(32);
+        if (globaltimer_ns() - t_idle > 3000000000ull) {
+          if (lane == 0) atomicExch(&cta->helper[m], -1);
+          return;
+        }
+      }
+    }
+  }
+}
+
 // PANOCEngine::step.  Returns true to continue.
 template <class DM>
 __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, int lane, const Problem &pb,
-                           Lane &z, Uni &U, double tolerance) {
+                           Lane &z, Uni &U, double tolerance, HelpCtl &hc) {
   if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
   compute_fpr(z, U);
   if (U.norm_fpr < tolerance) {
     const double r0 = fma(U.gamma, z.g0 - z.gp0, z.f0), r1 = fma(U.gamma, z.g1 - z.gp1, z.f1);
     if (sqrt(wsum(pdot(r0, r1, r0, r1))) < U.akkt_tol) return false;
   }
-  // update_lipschitz_constant
+  // update_lipschitz_constant (+ lbfgs_direction).  With a helper the Lipschitz check
+  // psi(u_half) runs on the helper while this warp already updates / applies L-BFGS on the
+  // current residual; if the check then asks for backtracking, the speculative L-BFGS state
+  // is rolled back and the sequential path below runs unchanged.
+  bool lbfgs_done = false;
   {
-    double cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
+    double cost_half;
+    if (help_available(hc)) {
+      help_post(hc, sm, lane, DM::N(g), z.h0, z.h1, pb.c, 0, 0.0);
+      const int s_first = U.lb_first, s_head = U.lb_head, s_active = U.lb_active;
+      const double s_gamma = U.lb_gamma, s_os0 = z.os0, s_os1 = z.os1, s_og0 = z.og0, s_og1 = z.og1;
+      lbfgs_update<DM>(g, sm, z, U, lane);
+      if (U.iteration > 0) { z.d0 = z.f0; z.d1 = z.f1; lbfgs_apply<DM>(g, sm, z, U, lane); }
+      EvalOut r;
+      if (hc.pending && help_wait(hc, sm, lane, DM::N(g), r)) {
+        cost_half = r.psi;
+        if (lane == 0) sm.ctx->n_cost++;
+      } else {
+        cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
+      }
+      const double rhs0 = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
+                          (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
+      if (cost_half > rhs0 && U.L < MAX_LIPSCHITZ_CONSTANT) {  // speculation lost
+        U.lb_first = s_first; U.lb_head = s_head; U.lb_active = s_active; U.lb_gamma = s_gamma;
+        z.os0 = s_os0; z.os1 = s_os1; z.og0 = s_og0; z.og1 = s_og1;
+      } else {
+        lbfgs_done = true;
+      }
+    } else {
+      cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
+    }
     int it = 0;
     while (true) {
       const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
@@ -303,16 +470,18 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
     U.sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * U.gamma);
   }
   // lbfgs_direction
-  {
-    PROF_BEGIN(t0)
-    lbfgs_update<DM>(g, sm, z, U, lane);
-    PROF_END(t0, 2)
-  }
-  if (U.iteration > 0) {
-    PROF_BEGIN(t0)
-    z.d0 = z.f0; z.d1 = z.f1;
-    lbfgs_apply<DM>(g, sm, z, U, lane);
-    PROF_END(t0, 3)
+  if (!lbfgs_done) {
+    {
+      PROF_BEGIN(t0)
+      lbfgs_update<DM>(g, sm, z, U, lane);
+      PROF_END(t0, 2)
+    }
+    if (U.iteration > 0) {
+      PROF_BEGIN(t0)
+      z.d0 = z.f0; z.d1 = z.f1;
+      lbfgs_apply<DM>(g, sm, z, U, lane);
+      PROF_END(t0, 3)
+    }
   }
   if (U.iteration == 0) {
     // update_no_linesearch
@@ -340,19 +509,41 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       const double one_m = 1.0 - U.tau;
       p0 = fma(-U.tau, z.d0, fma(-one_m, z.f0, z.u0));
       p1 = fma(-U.tau, z.d1, fma(-one_m, z.f1, z.u1));
+      // with a helper: the next candidate (tau/2) is evaluated speculatively at the same time
+      bool posted = false;
+      double n0 = 0.0, n1 = 0.0;
+      if (nls < MAX_LINESEARCH_ITERATIONS && help_available(hc)) {
+        const double tau2 = U.tau / 2.0, one_m2 = 1.0 - tau2;
+        n0 = fma(-tau2, z.d0, fma(-one_m2, z.f0, z.u0));
+        n1 = fma(-tau2, z.d1, fma(-one_m2, z.f1, z.u1));
+        help_post(hc, sm, lane, DM::N(g), n0, n1, pb.c, 1, U.gamma);
+        posted = hc.pending;
+      }
       // cost, gradient, gradient step, half step and both envelope scalars in one evaluation
       PROF_BEGIN(t0)
-      const EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), p0, p1, pb.c,
-                                     pb.ya, pb.yw, nullptr, true, U.gamma);
+      EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), p0, p1, pb.c,
+                               pb.ya, pb.yw, nullptr, true, U.gamma);
       PROF_END(t0, 1)
       if (lane == 0) sm.ctx->n_grad++;
       U.cost = e.psi;
       z.g0 = e.gv; z.g1 = e.gw; z.s0 = e.s0; z.s1 = e.s1; z.h0 = e.h0; z.h1 = e.h1;
-      const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+      double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
       U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
       U.tau /= 2.0;
       nls++;
+      if (posted && help_wait(hc, sm, lane, DM::N(g), e)) {  // the helper's evaluation is the one at this tau
+        if (lane == 0) sm.ctx->n_grad++;
+        p0 = n0; p1 = n1;
+        U.cost = e.psi;
+        z.g0 = e.gv; z.g1 = e.gw;
+        gradient_and_half_step(g, z, U, p0, p1);  // same s = p - gamma g, h = proj(s) the evaluation formed
+        lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+        U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
+        if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
+        U.tau /= 2.0;
+        nls++;
+      }
     }
     z.u0 = p0; z.u1 = p1;
   }
@@ -368,7 +559,7 @@ __device__ __forceinline__ void panoc_reset(Uni &U) {
 // One scene, start to finish.
 template <class DM>
 __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs &A, int scene,
-                            int lane, unsigned long long *wstats) {
+                            int lane, unsigned long long *wstats, HelpCtl &hc) {
   const int N = g.N;
   const bool act = lane < N;
   const unsigned long long t_start = globaltimer_ns();
@@ -408,6 +599,9 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     num_outer++;
     pb.ya = clipd(pb.ya, -1e12, 1e12);
     pb.yw = clipd(pb.yw, -1e12, 1e12);
+    help_drain(hc, sm, lane, N);
+    if (act) sm.yrow[lane] = make_double2(pb.ya, pb.yw);  // what a helper evaluates with
+    __syncwarp();
     // ---------------- inner problem: PANOCOptimizer::solve
     int inner_status;
     {
@@ -438,7 +632,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
       int num_iter = 0;
       bool cont = true;
       while (true) {
-        const bool flag = panoc_step<DM>(g, sm, lane, pb, z, U, g.tol);
+        const bool flag = panoc_step<DM>(g, sm, lane, pb, z, U, g.tol, hc);
         if (!(flag && cont)) break;
         num_iter++;
         cont = num_iter < g.max_inner;
@@ -496,6 +690,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
   if (exit_status != TTMPC_NOT_FINITE && num_outer == g.max_outer)
     exit_status = TTMPC_NOT_CONVERGED_ITERATIONS;
 
+  help_drain(hc, sm, lane, N);  // no evaluation on this scene's tables may still be in flight
   // ---------------- results
   if (act) {
     A.u[(size_t)scene * 2 * N + 2 * lane] = z.u0;
@@ -547,6 +742,14 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
   const WarpSmem sm = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
   const int gwarp = blockIdx.x * g.warps_per_block + warp;
   double *dyn = A.dyn_scratch + (size_t)gwarp * DYN_FIELDS * g.Ndyn * g.N;
+  CtaHelp *cta = reinterpret_cast<CtaHelp *>(smem_raw + (size_t)g.warps_per_block * g.smem_per_warp);
+  if (threadIdx.x < 8) { cta->busy[threadIdx.x] = 0; cta->helper[threadIdx.x] = -1; }
+  __syncthreads();
+  HelpCtl hc;
+  hc.enabled = A.helpers != 0;
+  hc.slot = &cta->helper[warp];
+  hc.pending = false;
+  if (lane == 0) sm.hhdr->state = 0;
   unsigned long long wstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   while (true) {
     int scene = 0;
@@ -570,9 +773,14 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
       __threadfence();
     }
     stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
-    solve_scene<DM>(g, sm, A, scene, lane, wstats);
+    if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 1;
+    hc.enabled = A.helpers != 0;
+    solve_scene<DM>(g, sm, A, scene, lane, wstats, hc);
+    if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 0;
     __syncwarp();
   }
+  // out of scenes: help the CTA-mates that still own one
+  if (A.helpers) helper_loop<DM>(g, A, cta, smem_raw, warp, lane);
   if (lane == 0 && A.stats) {
     for (int i = 0; i < 8; i++)
       if (wstats[i]) atomicAdd(A.stats + i, wstats[i]);
@@ -702,7 +910,7 @@ static cudaError_t set_smem(K kernel, size_t smem) {
 }
 
 cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block + sizeof(CtaHelp);
   cudaError_t e;
   if (is_default_dims(g)) {
     if ((e = set_smem(solve_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
@@ -726,7 +934,7 @@ cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream
   return cudaGetLastError();
 }
 cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm) {
-  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block + sizeof(CtaHelp);
   cudaError_t e;
   if (is_default_dims(g)) {
     if ((e = set_smem(solve_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
