@@ -24,4 +24,14 @@ nc, ng, nb, it, cyc_c, cyc_g, cyc_l, cyc_t = list(out)
 print(f"scenes {n}: cost evals {nc} grad evals {ng} panoc iters {it}")
 print(f"cycles/cost eval {cyc_c/max(nc,1):.0f}  cycles/grad eval {cyc_g/max(ng,1):.0f}  lbfgs cycles/iter {cyc_l/max(it,1):.0f}")
 print(f"share of solve cycles: cost evals {100*cyc_c/cyc_t:.1f}%  grad evals {100*cyc_g/cyc_t:.1f}%  lbfgs {100*cyc_l/cyc_t:.1f}%  rest {100*(cyc_t-cyc_c-cyc_g-cyc_l)/cyc_t:.1f}%")
+try:
+    lib.ttmpc_read_stats24.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    o24 = (C.c_ulonglong * 24)()
+    s.run_device(dp, bufs); torch.cuda.synchronize()
+    lib.ttmpc_read_stats24(o24, 1)
+    ev = o24[0] + o24[1]
+    names = ["rollout", "refpath", "speed+fleet", "dynamic", "terminal+static", "accel/ALM", "S+F2", "gradient+adjoint", "reduction"]
+    print("eval sections, cycles per evaluation:", {n: round(o24[8 + i] / max(ev, 1)) for i, n in enumerate(names)})
+except Exception as ex:
+    print("no eval section profile:", ex)
 print(f"total cycles per panoc iteration {cyc_t/max(it,1):.0f}; evals per iteration {(nc+ng)/max(it,1):.2f}")

@@ -120,8 +120,8 @@ static int get_ws(Workspace **out) {
   w.device = dev;
   CUDA_TRY(cudaDeviceGetAttribute(&w.sm_count, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaMalloc(&w.work_counter, 64));
-  CUDA_TRY(cudaMalloc(&w.stats, 64));
-  CUDA_TRY(cudaMemset(w.stats, 0, 64));
+  CUDA_TRY(cudaMalloc(&w.stats, 192));
+  CUDA_TRY(cudaMemset(w.stats, 0, 192));
   CUDA_TRY(cudaMalloc(&w.ready, 64));
   CUDA_TRY(cudaHostAlloc(&w.h_ready, sizeof(int) * 4096, cudaHostAllocDefault));
   CUDA_TRY(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
@@ -198,6 +198,7 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
   const char *nh = std::getenv("TTMPC_NO_HELPERS");
   SolveArgs A;
+  A.eprof = w->stats + 8;  // stats block is 24 x u64: [0..7] counters, [8..17] eval sections
   A.helpers = (nh && nh[0] == '1') ? 0 : 1;  // TTMPC_NO_HELPERS=1 disables the tail helpers
   A.ready = d_ready; A.timeout_flag = d_ready ? w->ready + 1 : nullptr;
   A.p = d_p; A.c0 = d_c0; A.u = res->u; A.y = res->y; A.cost = res->cost;
@@ -213,6 +214,16 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
 // Cumulative device-side counters since the last reset:
 // [0] cost-only evaluations [1] cost+gradient evaluations [2] dynamic-obstacle
 // bodies executed [3] PANOC iterations.  Synchronises the device.
+extern "C" int ttmpc_read_stats24(unsigned long long out[24], int reset) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace *w;
+  int rc = get_ws(&w);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, w->stats, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 192));
+  return TTMPC_OK;
+}
 extern "C" int ttmpc_read_stats8(unsigned long long out[8], int reset) {
   std::lock_guard<std::mutex> lk(g_mu);
   Workspace *w;
@@ -220,7 +231,7 @@ extern "C" int ttmpc_read_stats8(unsigned long long out[8], int reset) {
   if (rc) return rc;
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(out, w->stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 64));
+  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 192));
   return TTMPC_OK;
 }
 extern "C" int ttmpc_read_stats(unsigned long long out[4], int reset) {
@@ -230,7 +241,7 @@ extern "C" int ttmpc_read_stats(unsigned long long out[4], int reset) {
   if (rc) return rc;
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(out, w->stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 64));
+  if (reset) CUDA_TRY(cudaMemset(w->stats, 0, 192));
   return TTMPC_OK;
 }
 

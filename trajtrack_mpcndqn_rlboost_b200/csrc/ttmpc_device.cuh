@@ -159,8 +159,14 @@ struct WarpCtx {
   long long n_cost, n_grad, n_body;  // evaluation counters (lane 0 view)
   int nstc_active;                   // static obstacles that can ever be non-zero
   float fleet_thr;                   // fp32 contact prefilter threshold (padded d^2)
+  // box-guarded compaction: obstacles / robots whose bounding circles never meet the box
+  // |p - start|_inf < box_half are skipped while every rolled-out position stays in the box
+  double box_half;
+  unsigned long long dyn_live;       // bit j: dynamic obstacle j can matter inside the box
+  unsigned fleet_live;               // bit j: other robot j can matter inside the box
 #ifdef TTMPC_PROFILE
   long long prof[8];                 // cycles per phase (diagnostic build only)
+  long long eprof[10];               // cycles per section of eval_psi
 #endif
 };
 
@@ -275,6 +281,7 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
     c->n_cost = 0; c->n_grad = 0; c->n_body = 0;
 #ifdef TTMPC_PROFILE
     for (int i = 0; i < 8; i++) c->prof[i] = 0;
+    for (int i = 0; i < 10; i++) c->eprof[i] = 0;
 #endif
   }
   // reference-path segments: path_ref has N+1 points, last duplicated (l.190-191)
@@ -364,8 +371,39 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
       sm.dynb[3 * t] = (float)cx; sm.dynb[3 * t + 1] = (float)cy; sm.dynb[3 * t + 2] = r2f;
     }
   }
+  // live masks of the box-guarded compaction (NaN / inf coordinates stay live)
+  {
+    const double x0 = p[g.off_s], y0 = p[g.off_s + 1];
+    const double vm = fmax(fabs(g.vmax), fabs(g.vmin));
+    const double bh = 2.0 * g.N * g.ts * vm + 1.0;
+    unsigned long long dl = 0;
+    for (int t = lane; t < npair; t += 32) {
+      const int j = t / g.N;
+      const double *e = od + (size_t)t * 6;
+      const double rmax = fmax(fmax(fabs(e[2] + 1e-6), fabs(e[3] + 1e-6)),
+                               fmax(fabs(e[2] + g.margin + 1e-6), fabs(e[3] + g.margin + 1e-6))) * 1.001 + 1e-3;
+      const bool outside = fabs(e[0] - x0) > bh + rmax || fabs(e[1] - y0) > bh + rmax;
+      if (!outside) dl |= 1ull << j;
+    }
+    unsigned fl = 0;
+    const double dveh = sqrt(g.veh_d2) * 1.001 + 1e-3;
+    for (int t = lane; t < g.Nother * g.N; t += 32) {
+      const int j = t / g.N;
+      const bool outside = fabs(cpar[(size_t)t * 3] - x0) > bh + dveh || fabs(cpar[(size_t)t * 3 + 1] - y0) > bh + dveh;
+      if (!outside) fl |= 1u << j;
+    }
+    const unsigned dlo = __reduce_or_sync(FULL, (unsigned)dl), dhi = __reduce_or_sync(FULL, (unsigned)(dl >> 32));
+    fl = __reduce_or_sync(FULL, fl);
+    if (lane == 0) { c->box_half = bh; c->dyn_live = ((unsigned long long)dhi << 32) | dlo; c->fleet_live = fl; }
+  }
   __syncwarp();
 }
+
+#ifdef TTMPC_PROFILE
+#define EPROF(slot) { const long long tt_ = clock64(); if (lane == 0 && !Dalt) sm.ctx->eprof[slot] += tt_ - ep_t; ep_t = tt_; }
+#else
+#define EPROF(slot)
+#endif
 
 // ---------------------------------------------------------------- evaluation
 struct EvalOut {
@@ -423,6 +461,9 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   const int lk = act ? lane : N - 1;  // table column this lane reads
   const double ts = g.ts;
 
+#ifdef TTMPC_PROFILE
+  long long ep_t = clock64();
+#endif
   // ---- rollout (motion_model.py:153-176; RK4 of the unicycle = Simpson in theta):
   //      theta and position are prefix sums over the lanes
   const double tw = ts * w;
@@ -451,30 +492,54 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   const double TH = cx->th0 + th_in;
   if (st_out && act) { st_out[3 * lane] = X; st_out[3 * lane + 1] = Y; st_out[3 * lane + 2] = TH; }
 
+  // every rolled-out position inside the scene's box?  then only the "live" robots / obstacles
+  // can contribute (the others are farther than their radius from every point of the box)
+  const bool in_box = __all_sync(FULL, fabs(X - cx->x0) < cx->box_half && fabs(Y - cx->y0) < cx->box_half);
+  EPROF(0)
   double cost;               // this lane's share of f
   double gx = 0.0, gy = 0.0; // d psi / d position_{k+1}
   double S_loc = 0.0, gSx = 0.0, gSy = 0.0;
 
-  // ---- reference-path deviation (l.124-139, 202): min over the remaining segments
+  // ---- reference-path deviation (l.124-139, 202): min over the remaining segments j >= k.
+  //      Step k has N - k segments (lane 0 the most); the 32 - N lanes beyond the horizon take
+  //      the upper half of the ranges of the first 32 - N steps, so the loop is ~N/2 long.
+  //      min is exact and ties go to the lower segment index, as in the sequential fold.
   {
-    double dmin = INFINITY; int jmin = lk;
+    const int nh = 32 - N;                                  // lanes available as helpers
+    const bool is_helper = !act && (lane - N) < N;          // helper of step lane - N
+    const int kq = is_helper ? lane - N : lk;               // the step whose position this lane tests
+    const double Xq = __shfl_sync(FULL, X, kq), Yq = __shfl_sync(FULL, Y, kq);
+    const bool split = kq < nh;                             // this step's range is shared
+    const int mid = kq + (N - kq + 1) / 2;
+    const int lo = is_helper ? mid : kq;
+    const int hi = (act && split) ? mid : N;
+    const int cnt = (act || is_helper) ? hi - lo : 0;
+    const int trips = (nh >= N) ? (N + 1) / 2 : max((N + 1) / 2, N - nh);
+    double dmin = INFINITY; int jmin = lo;
     const double2 *segv = reinterpret_cast<const double2 *>(sm.seg);
 #pragma unroll 2
-    for (int j = 0; j < N; j++) {
+    for (int t = 0; t < trips; t++) {
+      const int j = min(lo + t, N - 1);
       const double2 s1 = segv[3 * j], sd = segv[3 * j + 1];
       const double inv = sm.seg[6 * j + 4];
-      const double px = X - s1.x, py = Y - s1.y;
+      const double px = Xq - s1.x, py = Yq - s1.y;
       const double t_hat = fma(py, sd.y, px * sd.x) * inv;
-      const double t = clamp01(t_hat);
-      const double qx = fma(t, sd.x, -px), qy = fma(t, sd.y, -py);
+      const double tt = clamp01(t_hat);
+      const double qx = fma(tt, sd.x, -px), qy = fma(tt, sd.y, -py);
       const double d2 = fma(qy, qy, qx * qx);
-      const bool take = (j >= lk) && !(dmin <= d2);  // first minimum wins ties
+      const bool take = (t < cnt) && !(dmin <= d2);  // first minimum wins ties
       dmin = take ? d2 : dmin;
       jmin = take ? j : jmin;
     }
+    {  // fold the helper's half into the owner (owner = lower indices wins ties)
+      const int src = (act && split) ? N + lane : lane;
+      const double dh = __shfl_sync(FULL, dmin, src);
+      const int jh = __shfl_sync(FULL, jmin, src);
+      if (act && split && !(dmin <= dh)) { dmin = dh; jmin = jh; }
+    }
     cost = dmin * cx->qrpd;
     if (GRAD) {
-      const int j = jmin;
+      const int j = act ? jmin : N - 1;
       const double2 s1 = segv[3 * j], sd = segv[3 * j + 1];
       const double inv = sm.seg[6 * j + 4];
       const double px = X - s1.x, py = Y - s1.y;
@@ -487,6 +552,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       gy = cx->qrpd * (2.0 * fma(cs, sd.y, -qy));
     }
   }
+  EPROF(1)
   // ---- speed reference + control action (l.203-204)
   const double vr = sm.vref[lk];
   {
@@ -501,13 +567,15 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   {
     unsigned hit = 0;
     const float thr = cx->fleet_thr;
-#pragma unroll 2
-    for (int j = 0; j < Nother; j++) {
+    unsigned todo = in_box ? cx->fleet_live : (Nother >= 32 ? 0xffffffffu : ((1u << Nother) - 1u));
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
       const float2 o = sm.fleet[j * N + lk];
       const float exf = Xf - o.x, eyf = Yf - o.y;
       hit |= (!((exf * exf + eyf * eyf) >= thr) ? 1u : 0u) << j;
     }
-    if (__any_sync(FULL, hit != 0)) {
+    if (__builtin_expect(__any_sync(FULL, hit != 0), 0)) {
       const double *cp = cx->p + g.off_c + 3 * lk;
       double acc = 0.0, fx = 0.0, fy = 0.0;
       while (hit) {
@@ -524,19 +592,22 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       if (GRAD) { gx = fma(1000.0, fx, gx); gy = fma(1000.0, fy, gy); }
     }
   }
+  EPROF(2)
   // ---- dynamic obstacles (l.225-237): hard penalty D_j and soft cost.
   //      fp32 bounding test from shared memory first; the exact fp64 body (global
   //      table) only runs for pairs that can be non-zero.
   unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
   {
     unsigned long long near_mask = 0;
-#pragma unroll 3
-    for (int j = 0; j < Ndyn; j++) {
+    unsigned long long todo = in_box ? cx->dyn_live : (Ndyn >= 64 ? ~0ull : ((1ull << Ndyn) - 1ull));
+    while (todo) {
+      const int j = __ffsll((long long)todo) - 1;
+      todo &= todo - 1;
       const float *b = sm.dynb + 3 * (j * N + lk);
       const float exf = Xf - b[0], eyf = Yf - b[1];
       near_mask |= (unsigned long long)((exf * exf + eyf * eyf) < b[2] ? 1u : 0u) << j;
     }
-    if (__any_sync(FULL, near_mask != 0)) {
+    if (__builtin_expect(__any_sync(FULL, near_mask != 0), 0)) {
       const double *T = cx->dyn;
       double soft = 0.0;
       int bodies = 0;
@@ -577,7 +648,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   }
   // hard terms are rare: one vote for the whole loop, per-obstacle sums only when needed
   const bool any_hard = __any_sync(FULL, hard_mask != 0);
-  if (any_hard) {
+  if (__builtin_expect(any_hard, 0)) {
     const unsigned lo = __reduce_or_sync(FULL, (unsigned)hard_mask);
     const unsigned hi = __reduce_or_sync(FULL, (unsigned)(hard_mask >> 32));
     const unsigned long long warp_hard = ((unsigned long long)hi << 32) | lo;
@@ -600,6 +671,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     }
     __syncwarp();
   }
+  EPROF(3)
   // ---- terminal cost (l.242)
   double gt = 0.0;
   if (lane == N - 1) {
@@ -628,7 +700,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       }
       in_mask |= (inside > 0.0 ? 1u : 0u) << i;
     }
-    if (__any_sync(FULL, in_mask != 0)) {
+    if (__builtin_expect(__any_sync(FULL, in_mask != 0), 0)) {
       while (in_mask) {
         const int i = __ffs(in_mask) - 1;
         in_mask &= in_mask - 1;
@@ -661,6 +733,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       }
     }
   }
+  EPROF(4)
   // ---- accelerations: cost (l.250-264) and the ALM set C = acc bounds
   double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
   if (lane == 0) { vp = cx->v_init; wp = cx->w_init; }
@@ -679,30 +752,32 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     cost = 0.0; gx = 0.0; gy = 0.0; S_loc = 0.0; gSx = 0.0; gSy = 0.0;
     aa = 0.0; aw = 0.0; ea = 0.0; ew = 0.0; alm = 0.0;
   }
+  EPROF(5)
   // ---- static sum: needed before the gradient (weight c * sum F2); zero in most evaluations
   double S = 0.0;
-  if (__any_sync(FULL, S_loc != 0.0)) S = wsum(S_loc);
+  if (__builtin_expect(__any_sync(FULL, S_loc != 0.0), 0)) S = wsum(S_loc);
   double f2sq = 0.0, sumF2 = 0.0;
-  if (any_hard) {
+  if (__builtin_expect(any_hard, 0)) {
 #pragma unroll 1
     for (int j = 0; j < Ndyn; j++) {
       const double F2j = S + Dv[j];
       f2sq = fma(F2j, F2j, f2sq);
       sumF2 += F2j;
     }
-  } else {  // every D_j is zero: F2_j = S + 0.0 = S (same operations, no loads)
+  } else if (__builtin_expect(S != 0.0, 0)) {  // every D_j is zero: F2_j = S + 0.0 = S (same operations, no loads)
 #pragma unroll 1
     for (int j = 0; j < Ndyn; j++) {
       f2sq = fma(S, S, f2sq);
       sumF2 += S;
     }
-  }
+  }  // S == 0 and no hard term: the loop would leave f2sq = sumF2 = +0
   EvalOut out;
   out.f2sq = f2sq; out.S = S; out.any_hard = any_hard;
   out.gv = 0.0; out.gw = 0.0;
   out.s0 = out.s1 = out.h0 = out.h1 = out.dd = out.g2 = 0.0;
   double ddp = 0.0, g2p = 0.0;
 
+  EPROF(6)
   if (GRAD) {
     double gv = 0.0, gw = 0.0;
     // hard-penalty gradient: c * sum_j F2_j * (grad S + grad D_j)
@@ -710,7 +785,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       const double cs_ = c * sumF2;
       gx = fma(cs_, gSx, gx);
       gy = fma(cs_, gSy, gy);
-      if (any_hard) {
+      if (__builtin_expect(any_hard, 0)) {
         unsigned long long mk = hard_mask;
         const double *T = cx->dyn;
         while (mk) {
@@ -763,10 +838,12 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
       g2p = pdot(gv, gw, gv, gw);
     }
   }
+  EPROF(7)
   // ---- one batched reduction: f, ALM distance (and the line-search scalars)
   const D4 r = wsum4v(cost, alm, ddp, g2p);
   out.f = r.a; out.dd = r.c; out.g2 = r.d;
   out.psi = r.a + c * r.b / 2 + c * f2sq / 2;
+  EPROF(8)
   return out;
 }
 

@@ -16,6 +16,7 @@ struct SolveArgs {
   long long *evals;     // [n][4] or null
   double *dyn_scratch;  // [total_warps][DYN_FIELDS*Ndyn*N]
   int *work_counter;    // dynamic scene queue
+  unsigned long long *eprof;  // [10] eval section cycles (diagnostic build) or null
   int helpers;          // 1: warps that run out of scenes help their CTA-mates (tail of a batch)
   int *timeout_flag;    // set to 1 if a wait on `ready` timed out (host then re-runs unstreamed)
   const int *ready;     // optional: number of scenes whose parameters have landed in d_p

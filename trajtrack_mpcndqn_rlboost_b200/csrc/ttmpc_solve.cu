@@ -416,7 +416,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
                            Lane &z, Uni &U, double tolerance, HelpCtl &hc) {
   if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
   compute_fpr(z, U);
-  if (U.norm_fpr < tolerance) {
+  if (__builtin_expect(U.norm_fpr < tolerance, 0)) {
     const double r0 = fma(U.gamma, z.g0 - z.gp0, z.f0), r1 = fma(U.gamma, z.g1 - z.gp1, z.f1);
     if (sqrt(wsum(pdot(r0, r1, r0, r1))) < U.akkt_tol) return false;
   }
@@ -427,7 +427,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   bool lbfgs_done = false;
   {
     double cost_half;
-    if (help_available(hc)) {
+    if (__builtin_expect(help_available(hc), 0)) {
       help_post(hc, sm, lane, DM::N(g), z.h0, z.h1, pb.c, 0, 0.0);
       const int s_first = U.lb_first, s_head = U.lb_head, s_active = U.lb_active;
       const double s_gamma = U.lb_gamma, s_os0 = z.os0, s_os1 = z.os1, s_og0 = z.og0, s_og1 = z.og1;
@@ -512,7 +512,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       // with a helper: the next candidate (tau/2) is evaluated speculatively at the same time
       bool posted = false;
       double n0 = 0.0, n1 = 0.0;
-      if (nls < MAX_LINESEARCH_ITERATIONS && help_available(hc)) {
+      if (__builtin_expect(nls < MAX_LINESEARCH_ITERATIONS && help_available(hc), 0)) {
         const double tau2 = U.tau / 2.0, one_m2 = 1.0 - tau2;
         n0 = fma(-tau2, z.d0, fma(-one_m2, z.f0, z.u0));
         n1 = fma(-tau2, z.d1, fma(-one_m2, z.f1, z.u1));
@@ -730,6 +730,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
 #endif
     wstats[6] += sm.ctx->prof[2] + sm.ctx->prof[3];
     wstats[7] += clock64() - t_clk0;
+    if (A.eprof) for (int i = 0; i < 10; i++) atomicAdd(A.eprof + i, (unsigned long long)sm.ctx->eprof[i]);
 #endif
   }
 }

@@ -122,6 +122,8 @@ def make_scenes(n: int, cfg: TtmpcConfig, seed: int = 0, n_static: int = 4, n_dy
 WORKLOADS = {
     # BASELINE.json configs[1]: 4096 scenes, default horizon, static polygon obstacles
     "static4096": dict(n=4096, n_static=4, n_dynamic=0, blocking_fraction=0.1, solver={}),
+    # default shapes with both obstacle kinds active (diagnostics / sweep reference point)
+    "mixed4096": dict(n=4096, n_static=4, n_dynamic=3, blocking_fraction=0.1, solver={}),
     # configs[2] per-GPU shard: moving ellipses, long iteration limits
     "dynamic8192": dict(n=8192, n_static=3, n_dynamic=4, blocking_fraction=0.1,
                         solver=dict(max_inner_iterations=2000, max_outer_iterations=20)),
