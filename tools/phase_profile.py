@@ -31,6 +31,7 @@ try:
     lib.ttmpc_read_stats24(o24, 1)
     ev = o24[0] + o24[1]
     names = ["rollout", "refpath", "speed+fleet", "dynamic", "terminal+static", "accel/ALM", "S+F2", "gradient+adjoint", "reduction"]
+    print("lbfgs apply cycles per iteration:", round(o24[17] / max(o24[3], 1)), " update+apply:", round(o24[6] / max(o24[3], 1)))
     print("eval sections, cycles per evaluation:", {n: round(o24[8 + i] / max(ev, 1)) for i, n in enumerate(names)})
 except Exception as ex:
     print("no eval section profile:", ex)

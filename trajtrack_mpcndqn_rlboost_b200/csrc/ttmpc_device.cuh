@@ -46,7 +46,6 @@ struct DevCfg {
 // Cody-Waite reduction by pi/2 (three fma steps, exact products) and the fdlibm
 // __kernel_sin / __kernel_cos minimax polynomials.  <= 1 ulp on |x| < 1e9.
 __host__ __device__ __forceinline__ void tt_sincos(double x, double *s, double *c) {
-  if (!(fabs(x) < 1.0e9)) { *s = x * 0.0 + NAN; *c = *s; return; }
   const double kd = rint(x * 6.36619772367581382433e-01);
   double r = fma(-kd, 1.5707963267948966e+00, x);
   r = fma(-kd, 6.123233995736766e-17, r);
@@ -65,12 +64,12 @@ __host__ __device__ __forceinline__ void tt_sincos(double x, double *s, double *
   pc = fma(z, pc, -1.38888888888741095749e-03);
   pc = fma(z, pc, 4.16666666666666019037e-02);
   const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
-  switch (q) {
-    case 0: *s = sr; *c = cr; break;
-    case 1: *s = cr; *c = -sr; break;
-    case 2: *s = -sr; *c = -cr; break;
-    default: *s = -cr; *c = sr; break;
-  }
+  // quadrant fix-up without branches: q odd swaps, bit 1 of q / q+1 negates
+  const bool swap = (q & 1) != 0;
+  const double sb = swap ? cr : sr, cb = swap ? sr : cr;
+  double so = (q & 2) ? -sb : sb, co = ((q + 1) & 2) ? -cb : cb;
+  if (!(fabs(x) < 1.0e9)) { so = x * 0.0 + NAN; co = so; }  // huge / non-finite argument
+  *s = so; *c = co;
 }
 
 // ---------------------------------------------------------------- warp utils
@@ -687,7 +686,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   //      flag, one vote, second pass over the flagged obstacles in the same order.
   {
     unsigned in_mask = 0;  // Nstcobs <= 32
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Nstc; i++) {
       const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
       double inside = 1.0;

@@ -730,6 +730,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
 #endif
     wstats[6] += sm.ctx->prof[2] + sm.ctx->prof[3];
     wstats[7] += clock64() - t_clk0;
+    sm.ctx->eprof[9] = sm.ctx->prof[3];  // L-BFGS apply alone (slot 6 holds update + apply)
     if (A.eprof) for (int i = 0; i < 10; i++) atomicAdd(A.eprof + i, (unsigned long long)sm.ctx->eprof[i]);
 #endif
   }
