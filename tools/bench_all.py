@@ -63,7 +63,7 @@ def main():
     _lib.check(_lib.load().ttmpc_measure_fp64_peak(C.byref(peak), None), "peak")
     rows = []
     # named workloads
-    for name in ("static4096", "dynamic8192"):
+    for name in ("static4096", "mixed4096", "dynamic8192"):
         w = t.scenes.WORKLOADS[name]
         cfg = t.Configurator().to_ttmpc(**w["solver"])
         p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],

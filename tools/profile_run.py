@@ -5,7 +5,8 @@ import torch
 import trajtrack_mpcndqn_rlboost_b200 as t
 name = sys.argv[1] if len(sys.argv) > 1 else "static4096"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-w = t.scenes.WORKLOADS[name]
+w = dict(t.scenes.WORKLOADS[name])
+if len(sys.argv) > 3: w["n"] = int(sys.argv[3])
 cfg = t.Configurator().to_ttmpc(**w["solver"])
 p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
                          blocking_fraction=w["blocking_fraction"])

@@ -161,6 +161,10 @@ static int grid_for(Workspace *w, const DevCfg &g, int n_scenes, int *grid) {
   CUDA_TRY(solve_occupancy(g, &bps));
   if (bps < 1) return fail(TTMPC_ERR_UNSUPPORTED, "configuration does not fit in shared memory");
   long long want = ((long long)n_scenes + g.warps_per_block - 1) / g.warps_per_block;
+  if (const char *e = std::getenv("TTMPC_MAX_BLOCKS_PER_SM")) {  // diagnostic: occupancy sweeps
+    const int v = std::atoi(e);
+    if (v >= 1 && v < bps) bps = v;
+  }
   long long cap = (long long)w->sm_count * bps;
   *grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
   return TTMPC_OK;

@@ -232,27 +232,32 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, 
   return (int)((b + 15) / 16 * 16);
 }
 
+// With compile-time dimensions (DimsDefault) every offset folds into the load / store
+// immediates: one base register instead of ~20 pointers and their address arithmetic.
+template <class DM>
 __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) {
   WarpSmem w;
   unsigned char *q = base;
+  const int N = DM::N(g), MEM = DM::mem(g), Nother = DM::Nother(g), Nstc = DM::Nstc(g),
+            nstcobs = 3 * DM::ne(g), Ndyn = DM::Ndyn(g);
   w.ctx = reinterpret_cast<WarpCtx *>(q); q += (sizeof(WarpCtx) + 15) / 16 * 16;
-  const int NP = g.N | 1;
-  w.lbs = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * NP;
-  w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(g.mem + 1) * NP;
+  const int NP = N | 1;
+  w.lbs = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(MEM + 1) * NP;
+  w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(MEM + 1) * NP;
   w.qrow = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)NP;
-  w.fleet = reinterpret_cast<float2 *>(q); q += (sizeof(float2) * (size_t)g.Nother * g.N + 15) / 16 * 16;
-  w.dynb = reinterpret_cast<float *>(q); q += (sizeof(float) * 3 * (size_t)g.Ndyn * g.N + 15) / 16 * 16;
-  w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 6 * g.N;
-  w.os = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.Nstc * g.nstcobs + 1) / 2 * 2);
-  w.D = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.Ndyn + 1) / 2 * 2);
-  w.vref = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.N + 1) / 2 * 2);
-  w.gsy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(g.mem + 1) * (g.mem + 1);
-  w.gyy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(g.mem + 1) * (g.mem + 1);
-  w.rho = reinterpret_cast<double *>(q); q += sizeof(double) * ((g.mem + 2) / 2 * 2);
-  w.alpha = reinterpret_cast<double *>(q); q += sizeof(double) * (2 * (g.mem + 1));
-  w.hreq = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.N;
-  w.hres = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.N;
-  w.yrow = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)g.N;
+  w.fleet = reinterpret_cast<float2 *>(q); q += (sizeof(float2) * (size_t)Nother * N + 15) / 16 * 16;
+  w.dynb = reinterpret_cast<float *>(q); q += (sizeof(float) * 3 * (size_t)Ndyn * N + 15) / 16 * 16;
+  w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 6 * N;
+  w.os = reinterpret_cast<double *>(q); q += sizeof(double) * ((Nstc * nstcobs + 1) / 2 * 2);
+  w.D = reinterpret_cast<double *>(q); q += sizeof(double) * ((Ndyn + 1) / 2 * 2);
+  w.vref = reinterpret_cast<double *>(q); q += sizeof(double) * ((N + 1) / 2 * 2);
+  w.gsy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(MEM + 1) * (MEM + 1);
+  w.gyy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(MEM + 1) * (MEM + 1);
+  w.rho = reinterpret_cast<double *>(q); q += sizeof(double) * ((MEM + 2) / 2 * 2);
+  w.alpha = reinterpret_cast<double *>(q); q += sizeof(double) * (2 * (MEM + 1));
+  w.hreq = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)N;
+  w.hres = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)N;
+  w.yrow = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)N;
   w.hhdr = reinterpret_cast<HelpHdr *>(q);
   return w;
 }
@@ -448,7 +453,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   // Dalt: a helper warp evaluating on another warp's scene tables brings its own scratch for
   // the per-obstacle hard sums (and does not touch the owner's counters)
   const DevCfg &g = *gp;
-  const WarpSmem sm = carve(smem_base, g);
+  const WarpSmem sm = carve<DM>(smem_base, g);
   double *const Dv = Dalt ? Dalt : sm.D;
   const int lane = threadIdx.x & 31;
   const double v = lane < DM::N(g) ? v_in : 0.0, w = lane < DM::N(g) ? w_in : 0.0;

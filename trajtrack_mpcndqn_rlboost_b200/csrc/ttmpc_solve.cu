@@ -11,6 +11,8 @@
 // butterfly all-reduces.
 #include "ttmpc_device.cuh"
 #include "ttmpc_launch.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace ttmpc {
 
@@ -343,7 +345,7 @@ template <class DM>
 __device__ void helper_loop(const DevCfg &g, const SolveArgs &A, CtaHelp *cta, unsigned char *smem_raw,
                             int warp, int lane) {
   const int W = g.warps_per_block;
-  const WarpSmem mine = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
+  const WarpSmem mine = carve<DM>(smem_raw + (size_t)warp * g.smem_per_warp, g);
   unsigned long long t_idle = globaltimer_ns();
   while (true) {
     int m = -1, any_busy = 0;
@@ -364,7 +366,7 @@ __device__ void helper_loop(const DevCfg &g, const SolveArgs &A, CtaHelp *cta, u
       continue;
     }
     unsigned char *base_m = smem_raw + (size_t)m * g.smem_per_warp;
-    const WarpSmem own = carve(base_m, g);
+    const WarpSmem own = carve<DM>(base_m, g);
     const int N = g.N;
     while (true) {
       int st = 0, alive = 1;
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
                                                     const __grid_constant__ SolveArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const WarpSmem sm = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
+  const WarpSmem sm = carve<DM>(smem_raw + (size_t)warp * g.smem_per_warp, g);
   const int gwarp = blockIdx.x * g.warps_per_block + warp;
   double *dyn = A.dyn_scratch + (size_t)gwarp * DYN_FIELDS * g.Ndyn * g.N;
   CtaHelp *cta = reinterpret_cast<CtaHelp *>(smem_raw + (size_t)g.warps_per_block * g.smem_per_warp);
@@ -795,7 +797,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevCf
                                                    const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const WarpSmem sm = carve(smem_raw + (size_t)warp * g.smem_per_warp, g);
+  const WarpSmem sm = carve<DM>(smem_raw + (size_t)warp * g.smem_per_warp, g);
   const int gwarp = blockIdx.x * g.warps_per_block + warp;
   const int nwarps = gridDim.x * g.warps_per_block;
   double *dyn = A.dyn_scratch + (size_t)gwarp * DYN_FIELDS * g.Ndyn * g.N;
@@ -837,12 +839,21 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevCf
 // 10-pair L-BFGS apply and a double division, each averaged over `reps` back-to-back calls.
 template <class DM>
 __global__ void __launch_bounds__(128, 3) probe_kernel(const __grid_constant__ DevCfg g, const double *p,
-                                                       double *dyn, long long *out, int reps) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x >= 32) return;
-  const WarpSmem sm = carve(smem_raw, g);
+                                                       double *dyn, long long *out, int reps,
+                                                       int warps) {
+  // `warps` warps of every CTA run the same measurement on their own copy of the scene
+  // (grid x warps > 1 shows how the latencies change when the SM is shared); block 0 /
+  // warp 0 reports
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const int lane = threadIdx.x & 31, warp_id = threadIdx.x >> 5;
+  if (warp_id >= warps) return;
+  unsigned char *smem_raw = smem_all + (size_t)warp_id * g.smem_per_warp;
+  const WarpSmem sm = carve<DM>(smem_raw, g);
   stage_scene(g, sm, p, dyn, lane);
+  {  // desynchronise the warps
+    const long long until = clock64() + ((blockIdx.x * 4 + warp_id) * 7919) % 9000;
+    while (clock64() < until) {}
+  }
   double v = lane < g.N ? 0.8 : 0.0, w = lane < g.N ? 0.05 : 0.0, acc = 0.0;
   long long t0 = clock64();
   for (int i = 0; i < reps; i++) {
@@ -878,7 +889,7 @@ __global__ void __launch_bounds__(128, 3) probe_kernel(const __grid_constant__ D
   double f = d;
   for (int i = 0; i < reps; i++) f = fma(f, 0.999, 1e-3);
   long long t7 = clock64();
-  if (lane == 0) {
+  if (lane == 0 && blockIdx.x == 0 && warp_id == 0) {
     out[0] = (t1 - t0) / reps; out[1] = (t2 - t1) / reps; out[2] = (t3 - t2) / reps;
     out[3] = (t4 - t3) / reps; out[4] = (t5 - t4) / reps; out[5] = (t6 - t5) / reps;
     out[6] = (t7 - t6) / reps; out[7] = (long long)(acc + z.d0 + d + f);
@@ -951,12 +962,15 @@ cudaError_t launch_probe(const DevCfg &g, const double *p, double *dyn, long lon
                          cudaStream_t st) {
   const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
   cudaError_t e;
+  int grid = 1, warps = 1;  // diagnostics: TTMPC_PROBE_GRID x TTMPC_PROBE_WARPS warps run the probe together
+  if (const char *s = std::getenv("TTMPC_PROBE_GRID")) grid = std::max(1, std::atoi(s));
+  if (const char *s = std::getenv("TTMPC_PROBE_WARPS")) warps = std::min(std::max(1, std::atoi(s)), g.warps_per_block);
   if (is_default_dims(g)) {
     if ((e = set_smem(probe_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
-    probe_kernel<DimsDefault><<<1, 128, smem, st>>>(g, p, dyn, out, reps);
+    probe_kernel<DimsDefault><<<grid, 128, smem, st>>>(g, p, dyn, out, reps, warps);
   } else {
     if ((e = set_smem(probe_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
-    probe_kernel<DimsRuntime><<<1, 128, smem, st>>>(g, p, dyn, out, reps);
+    probe_kernel<DimsRuntime><<<grid, 128, smem, st>>>(g, p, dyn, out, reps, warps);
   }
   return cudaGetLastError();
 }
