@@ -7,7 +7,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -f
              -Xcompiler -fPIC -Xcompiler -O2
 LIB       := $(PKG)/libttmpc.so
 ORACLE    := oracle/libttmpc_oracle.so
-CU        := $(CSRC)/ttmpc_solve.cu $(CSRC)/ttmpc_api.cu $(CSRC)/ttdqn.cu
+CU        := $(CSRC)/ttmpc_solve.cu $(CSRC)/ttmpc_api.cu $(CSRC)/ttmpc_fleet.cu $(CSRC)/ttdqn.cu
 HDRS      := include/ttmpc.h $(CSRC)/ttmpc_device.cuh $(CSRC)/ttmpc_launch.cuh
 
 all: $(LIB) $(ORACLE)
@@ -19,8 +19,8 @@ $(LIB): $(CU:.cu=.o)
 	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $^ -lcudart
 
 # -ffp-contract=off: plain IEEE mul/add like the reference's Rust/casadi-C build
-$(ORACLE): oracle/ttmpc_oracle.c oracle/ttdqn_oracle.c oracle/ttmpc_oracle.h include/ttmpc.h
-	$(CC) -O2 -fPIC -shared -ffp-contract=off -Wall -o $@ oracle/ttmpc_oracle.c oracle/ttdqn_oracle.c -lm -lpthread
+$(ORACLE): oracle/ttmpc_oracle.c oracle/ttdqn_oracle.c oracle/ttfleet_oracle.c oracle/ttmpc_oracle.h include/ttmpc.h
+	$(CC) -O2 -fPIC -shared -ffp-contract=off -Wall -o $@ oracle/ttmpc_oracle.c oracle/ttdqn_oracle.c oracle/ttfleet_oracle.c -lm -lpthread
 
 clean:
 	rm -f $(CSRC)/*.o $(LIB) $(ORACLE)

@@ -223,6 +223,73 @@ int ttdqn_observe_act_host(const ttdqn_scene_layout *lay, const ttdqn_qnet *qnet
                            float *h_ext, float *h_q, int *h_action,
                            double *h_seg_dist, double *h_ray_dist);
 
+/* ------------------------------------------------------------------------
+ * Fleet step: the caller side of the solve, batched on the device.
+ *
+ * One control step of n independent robots, each following the reference's
+ * InterfaceMpc.get_action -> TrajectoryGenerator.run_step sequence
+ * (src/interface_mpc.py:80-92, src/mpc_traj_tracker/trajectory_generator.py:203-274):
+ *
+ *   pack    : termination test (check_termination_condition, :158-164), closest point of
+ *             the global reference trajectory in the window [idx-1, idx+5) and the N
+ *             reference states from there (get_local_ref_traj, :203-230), speed
+ *             reference from the distance to the goal (:248-255), dynamic-obstacle rows
+ *             extrapolated from two consecutive positions (main.py:80-89,
+ *             est_dyn_obs_positions), and the packed parameter vector in the block
+ *             order of :257-260.
+ *   solve   : ttmpc_solve_batch_device.
+ *   advance : state <- unicycle RK4 step with the first control (run_solver, :291-294;
+ *             motion_model.py:153-176), last action, solver failure flag
+ *             (NotFiniteComputation -> the reference raises), obstacle positions moved by
+ *             their per-step displacement.
+ *
+ * All pointers are device pointers unless the struct member says otherwise; in/out
+ * members persist between steps, so K steps run without touching the host.
+ * ------------------------------------------------------------------------ */
+enum {
+  TTMPC_FLEET_RUNNING = 0,  /* get_action returned an action                      */
+  TTMPC_FLEET_REACHED = 1,  /* check_termination_condition: get_action -> None    */
+  TTMPC_FLEET_FAILED = 2    /* solver error (the reference raises RuntimeError)   */
+};
+typedef struct ttmpc_fleet {
+  int n;            /* robots                                                         */
+  int ref_stride;   /* rows per robot in ref_traj                                     */
+  double *state;    /* [n][3] x y theta, in/out                                       */
+  const double *goal;     /* [n][3]                                                   */
+  double *last_u;   /* [n][2] last applied action, in/out (zeros before the first)    */
+  int *idx_ref;     /* [n] index into the global reference trajectory, in/out         */
+  int *status;      /* [n] TTMPC_FLEET_*, in/out (robots not RUNNING are left alone)  */
+  const double *ref_traj; /* [n][ref_stride][3] get_global_ref_traj output            */
+  const int *ref_len;     /* [n] valid rows                                           */
+  const double *stc;      /* static half-space rows: [n][Nstcobs*nstcobs], or one
+                             shared row block when stc_shared != 0                   */
+  int stc_shared;
+  int n_dyn_live;   /* moving obstacles described by dyn_cur / dyn_last (<= Ndynobs)  */
+  int action_steps; /* config.action_steps; only 1 is supported                       */
+  int _pad;
+  const double *other;    /* [n][ns*N*Nother] other-robot predictions or NULL (zeros) */
+  const double *dyn;      /* [n][Ndynobs*ndynobs*N] ready-made rows or NULL           */
+  double *dyn_cur;  /* [n][n_dyn_live][2] current obstacle positions (in/out) or NULL */
+  double *dyn_last; /* [n][n_dyn_live][2] positions one step earlier (in/out)         */
+  const double *dyn_disp; /* [n][n_dyn_live][2] displacement per step (advance)       */
+  double dyn_size;  /* rx = ry of the extrapolated rows (main.py:32 DYN_OBS_SIZE)     */
+  double tuning[10];      /* q block (set_work_mode, trajectory_generator.py:117-131) */
+  double base_speed, low_speed;
+  double stc_weight, dyn_weight;
+} ttmpc_fleet;
+
+/* d_p [n][np] is written for every robot (robots that are not RUNNING keep packing from
+ * their frozen state, so the batch stays dense). */
+int ttmpc_fleet_pack_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet, double *d_p,
+                            void *stream);
+/* d_u [n][nu*N] solutions, d_exit_status [n] of the solve that used d_p. */
+int ttmpc_fleet_advance_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet,
+                               const double *d_u, const int *d_exit_status, void *stream);
+/* pack + solve (cold start, like run_step with initial_guess=None; multipliers carried in
+ * res->y when use_y0 != 0, like the reference's Solver object) + advance, on `stream`. */
+int ttmpc_fleet_step_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet, double *d_p,
+                            int use_y0, const ttmpc_result *res, void *stream);
+
 /* Cumulative device-side counters since the last reset: [0] cost-only
  * evaluations, [1] cost+gradient evaluations, [2] dynamic-obstacle bodies that
  * passed the bounding test, [3] PANOC iterations.  Synchronises the device.   */

@@ -72,6 +72,12 @@ int ttmpc_oracle_solve_batch(const ttmpc_config *cfg, int n, const double *p,
 void ttmpc_oracle_rollout(const ttmpc_config *cfg, const double *u, const double *p,
                           double *states);
 
+/* Fleet step (caller side of the solve), host pointers in ttmpc_fleet; see ttfleet_oracle.c.
+ * use_libm = 1: libm hypot/sin/cos like the reference's Python; 0: the device's arithmetic. */
+void ttfleet_oracle_pack(const ttmpc_config *cfg, const ttmpc_fleet *fleet, double *p, int use_libm);
+void ttfleet_oracle_advance(const ttmpc_config *cfg, const ttmpc_fleet *fleet, const double *u,
+                            const int *exit_status, int use_libm);
+
 /* DQN companion oracle: one env. */
 void ttdqn_oracle_observe(const ttdqn_scene_layout *lay, const double *agent,
                           const double *poly_xy, const int *poly_off,

@@ -11,7 +11,7 @@ import subprocess
 
 import numpy as np
 
-from trajtrack_mpcndqn_rlboost_b200._lib import TtmpcConfig, TtmpcResult, TtdqnLayout, TtdqnQnet
+from trajtrack_mpcndqn_rlboost_b200._lib import TtmpcConfig, TtmpcResult, TtdqnLayout, TtdqnQnet, TtmpcFleet
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_PATH = os.path.join(ROOT, "oracle", "libttmpc_oracle.so")
@@ -28,7 +28,7 @@ _lib = None
 
 
 def build():
-    src = [os.path.join(ROOT, "oracle", f) for f in ("ttmpc_oracle.c", "ttdqn_oracle.c")]
+    src = [os.path.join(ROOT, "oracle", f) for f in ("ttmpc_oracle.c", "ttdqn_oracle.c", "ttfleet_oracle.c")]
     subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", ORACLE_PATH,
                            *src, "-lm", "-lpthread"])
 
@@ -52,6 +52,8 @@ def load():
         lib.ttmpc_oracle_eval_warp.argtypes = [CFG, VP, VP, D, VP, VP, VP, VP, VP]
         lib.ttmpc_oracle_sincos.argtypes = [D, C.POINTER(D), C.POINTER(D)]
         lib.ttdqn_oracle_observe_act.argtypes = [C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet), I] + [VP] * 12
+        lib.ttfleet_oracle_pack.argtypes = [CFG, C.POINTER(TtmpcFleet), VP, I]
+        lib.ttfleet_oracle_advance.argtypes = [CFG, C.POINTER(TtmpcFleet), VP, VP, I]
         _lib = lib
     return _lib
 
@@ -142,3 +144,62 @@ def observe_act(lay, weights, agent, xy, off, sol, cnt, internal=None, old_ext=N
                                  _p(cnt), _p(internal), _p(old_ext), _p(ext), _p(q), _p(act), _p(seg),
                                  _p(ray))
     return dict(ext=ext, q=q, action=act, seg=seg, ray=ray, old_ext=old_ext)
+
+
+class FleetHost:
+    """Host-side fleet state (numpy) for the fleet-step oracle; same members as struct ttmpc_fleet."""
+
+    def __init__(self, cfg, state, goal, ref_traj, ref_len, stc, tuning, base_speed, low_speed,
+                 stc_weight=1e3, dyn_weight=1e3, dyn_cur=None, dyn_disp=None, dyn_size=1.6, other=None):
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.cfg = cfg
+        self.state, self.goal = f64(state).copy(), f64(goal)
+        self.n = len(self.state)
+        self.last_u = np.zeros((self.n, 2))
+        self.idx_ref = np.zeros(self.n, dtype=np.int32)
+        self.status = np.zeros(self.n, dtype=np.int32)
+        self.ref_traj, self.ref_len = f64(ref_traj), np.ascontiguousarray(ref_len, dtype=np.int32)
+        self.stc = f64(stc)
+        self.stc_shared = 1 if self.stc.ndim == 1 else 0  # one row block for every robot, or [n][...]
+        self.tuning, self.base_speed, self.low_speed = list(tuning), float(base_speed), float(low_speed)
+        self.stc_weight, self.dyn_weight, self.dyn_size = float(stc_weight), float(dyn_weight), float(dyn_size)
+        self.other = None if other is None else f64(other)
+        self.dyn_cur = None if dyn_cur is None else f64(dyn_cur).copy()
+        self.dyn_last = None if dyn_cur is None else f64(dyn_cur).copy()
+        self.dyn_disp = None if dyn_disp is None else f64(dyn_disp)
+
+    def struct(self):
+        f = TtmpcFleet()
+        f.n, f.ref_stride = self.n, self.ref_traj.shape[1]
+        f.state, f.goal, f.last_u = _p(self.state), _p(self.goal), _p(self.last_u)
+        f.idx_ref, f.status = _p(self.idx_ref), _p(self.status)
+        f.ref_traj, f.ref_len, f.stc = _p(self.ref_traj), _p(self.ref_len), _p(self.stc)
+        f.stc_shared, f.action_steps = self.stc_shared, 1
+        f.n_dyn_live = 0 if self.dyn_cur is None else self.dyn_cur.shape[1]
+        f.other, f.dyn = _p(self.other), None
+        f.dyn_cur, f.dyn_last, f.dyn_disp = _p(self.dyn_cur), _p(self.dyn_last), _p(self.dyn_disp)
+        f.dyn_size = self.dyn_size
+        for i, v in enumerate(self.tuning):
+            f.tuning[i] = float(v)
+        f.base_speed, f.low_speed = self.base_speed, self.low_speed
+        f.stc_weight, f.dyn_weight = self.stc_weight, self.dyn_weight
+        return f
+
+
+def fleet_pack(fh: FleetHost, use_libm: bool):
+    lib = load()
+    n_p = 2 * fh.cfg.ns + fh.cfg.nu + fh.cfg.nq + fh.cfg.ns * fh.cfg.N_hor + fh.cfg.N_hor + \
+        fh.cfg.ns * fh.cfg.N_hor * fh.cfg.Nother + fh.cfg.Nstcobs * fh.cfg.nstcobs + \
+        fh.cfg.Ndynobs * fh.cfg.ndynobs * fh.cfg.N_hor + 2 * fh.cfg.N_hor
+    p = np.zeros((fh.n, n_p))
+    f = fh.struct()
+    lib.ttfleet_oracle_pack(C.byref(fh.cfg), C.byref(f), _p(p), 1 if use_libm else 0)
+    return p
+
+
+def fleet_advance(fh: FleetHost, u, exit_status, use_libm: bool):
+    lib = load()
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    es = None if exit_status is None else np.ascontiguousarray(exit_status, dtype=np.int32)
+    f = fh.struct()
+    lib.ttfleet_oracle_advance(C.byref(fh.cfg), C.byref(f), _p(u), _p(es), 1 if use_libm else 0)

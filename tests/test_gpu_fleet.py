@@ -1,0 +1,83 @@
+"""Fleet step on the GPU (through the C-ABI) against the CPU oracle: the packed parameter block
+and K closed-loop steps (pack -> solve -> advance), bit for bit."""
+import numpy as np
+import pytest
+
+import trajtrack_mpcndqn_rlboost_b200 as t
+from trajtrack_mpcndqn_rlboost_b200.fleet import work_mode
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(n, seed, **solver):
+    mc = t.Configurator()
+    fl = t.scenes.make_fleet(n, seed=seed)
+    fp = t.FleetPlanner(mc, fl["init"], fl["goal"], fl["paths"], mode="work", **solver)
+    fp.update_static_constraints(fl["static_polys"], per_robot=True)
+    fp.set_moving_obstacles(fl["moving_pos"], fl["moving_disp"])
+    tuning, base = work_mode(mc, "work")
+    fh = O.FleetHost(fp.cfg, fl["init"], fl["goal"], fp.ref_traj.cpu().numpy(), fp.ref_len.cpu().numpy(),
+                     fp.stc.cpu().numpy(), tuning, base, mc.low_speed, dyn_cur=fl["moving_pos"], dyn_disp=fl["moving_disp"])
+    return fp, fh
+
+
+def test_pack_bit_exact():
+    fp, fh = _make(96, seed=4)
+    # put a few robots next to their goals (speed-reference branch, termination test)
+    st = fp.state.cpu().numpy()
+    g = fp.goal.cpu().numpy()
+    st[:8, :2] = g[:8, :2] + np.linspace(0.0, 1.5, 8)[:, None] * 0.5
+    st[8:12, :2] = g[8:12, :2] + 0.01
+    fp.state.copy_(fp.torch.tensor(st)); fh.state[:] = st
+    fp.pack(); fp.torch.cuda.synchronize()
+    p_ref = O.fleet_pack(fh, use_libm=False)
+    assert np.array_equal(fp.p.cpu().numpy(), p_ref)
+    assert np.array_equal(fp.idx_ref.cpu().numpy(), fh.idx_ref)
+    assert np.array_equal(fp.status.cpu().numpy(), fh.status)
+    assert (fh.status[8:12] == 1).all() and (fh.status[12:] == 0).all()
+
+
+def test_closed_loop_bit_exact():
+    n, steps = 24, 4
+    fp, fh = _make(n, seed=9, max_inner_iterations=60, max_outer_iterations=4)
+    for k in range(steps):
+        fp.step()
+        fp.torch.cuda.synchronize()
+        p = O.fleet_pack(fh, use_libm=False)
+        assert np.array_equal(fp.p.cpu().numpy(), p), f"packed parameters differ at step {k}"
+        ref = O.solve_batch(fp.cfg, p, threads=8, warp=True)
+        assert np.array_equal(fp.u.cpu().numpy(), ref["u"]), f"controls differ at step {k}"
+        assert np.array_equal(fp.exit_status.cpu().numpy(), ref["exit_status"])
+        O.fleet_advance(fh, ref["u"], ref["exit_status"], use_libm=False)
+        assert np.array_equal(fp.state.cpu().numpy(), fh.state), f"states differ at step {k}"
+        assert np.array_equal(fp.last_u.cpu().numpy(), fh.last_u)
+        assert np.array_equal(fp.idx_ref.cpu().numpy(), fh.idx_ref)
+        assert np.array_equal(fp.status.cpu().numpy(), fh.status)
+        assert np.array_equal(fp.dyn_cur.cpu().numpy(), fh.dyn_cur)
+    moved = np.abs(fh.state[:, :2] - t.scenes.make_fleet(n, seed=9)["init"][:, :2]).max(axis=1)
+    assert (moved > 0.05).mean() > 0.8          # the robots do drive
+
+
+def test_fleet_matches_single_robot_mirror():
+    """One robot through FleetPlanner and through the InterfaceMpc mirror (host numpy around the
+    same solver): same packed vector on the first step, same state to rounding of libm vs device sincos."""
+    mc = t.Configurator()
+    fl = t.scenes.make_fleet(1, seed=21, n_moving=0)
+    fp = t.FleetPlanner(mc, fl["init"], fl["goal"], fl["paths"], mode="work")
+    fp.update_static_constraints(fl["static_polys"][0])
+    one = t.InterfaceMpc(mc)
+    one.initialization(fl["init"][0].copy(), fl["goal"][0].copy(), fl["paths"][0], mode="work")
+    one.update_static_constraints(fl["static_polys"][0])
+    ref_local, _ = one.get_local_ref_traj()
+    params = one._traj_gen.assemble_parameters(one.stc_constraints, one.dyn_constraints, one.other_robot_states, ref_local)
+    # set_work_mode('work') happens inside run_step; the fleet was built in that mode
+    fp.pack(); fp.torch.cuda.synchronize()
+    p_dev = fp.p.cpu().numpy()[0]
+    one._traj_gen.set_work_mode("work")
+    params = one._traj_gen.assemble_parameters(one.stc_constraints, one.dyn_constraints, one.other_robot_states, ref_local)
+    np.testing.assert_allclose(p_dev, np.array(params, dtype=np.float64), rtol=4e-16, atol=0)
+    action, pred, cost = one.get_action(ref_local, mode="work")
+    fp.step(); fp.torch.cuda.synchronize()
+    np.testing.assert_allclose(fp.state.cpu().numpy()[0], one.state, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(fp.last_u.cpu().numpy()[0], action, rtol=0, atol=1e-12)

@@ -9,7 +9,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "static4096"
 w = t.scenes.WORKLOADS[name]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else w["n"]
 cfg = t.Configurator().to_ttmpc(**w["solver"])
-p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
+p = t.scenes.make_scenes(max(n, w["n"]), cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
                          blocking_fraction=w["blocking_fraction"])[:n]
 s = t.BatchSolver(cfg)
 lib = _lib.load()

@@ -7,7 +7,8 @@ from .mpc_config import Configurator, num_params, param_offsets  # noqa: F401
 from .solver import BatchSolver, Solver, OptimizerSolution, BatchSolution, EXIT_STATUS_NAMES  # noqa: F401
 from .planner import TrajectoryGenerator, InterfaceMpc  # noqa: F401
 from .motion_model import unicycle_model  # noqa: F401
-from . import scenes, dqn, geometry  # noqa: F401
+from .fleet import FleetPlanner  # noqa: F401
+from . import scenes, dqn, geometry, fleet  # noqa: F401
 
 __all__ = ["Configurator", "BatchSolver", "Solver", "TrajectoryGenerator", "InterfaceMpc",
-           "unicycle_model", "scenes", "dqn", "geometry"]
+           "FleetPlanner", "unicycle_model", "scenes", "dqn", "geometry", "fleet"]

@@ -57,10 +57,27 @@ class TtdqnQnet(C.Structure):
     ]
 
 
+class TtmpcFleet(C.Structure):
+    """struct ttmpc_fleet: raw addresses (device for the product calls, host for the oracle)."""
+    _fields_ = [
+        ("n", C.c_int), ("ref_stride", C.c_int),
+        ("state", C.c_void_p), ("goal", C.c_void_p), ("last_u", C.c_void_p),
+        ("idx_ref", C.c_void_p), ("status", C.c_void_p), ("ref_traj", C.c_void_p),
+        ("ref_len", C.c_void_p), ("stc", C.c_void_p),
+        ("stc_shared", C.c_int), ("n_dyn_live", C.c_int), ("action_steps", C.c_int), ("_pad", C.c_int),
+        ("other", C.c_void_p), ("dyn", C.c_void_p), ("dyn_cur", C.c_void_p),
+        ("dyn_last", C.c_void_p), ("dyn_disp", C.c_void_p),
+        ("dyn_size", C.c_double), ("tuning", C.c_double * 10),
+        ("base_speed", C.c_double), ("low_speed", C.c_double),
+        ("stc_weight", C.c_double), ("dyn_weight", C.c_double),
+    ]
+
+
 # every symbol include/ttmpc.h declares, with its signature
 _VP, _I, _D = C.c_void_p, C.c_int, C.c_double
 _CFG, _RES = C.POINTER(TtmpcConfig), C.POINTER(TtmpcResult)
 _LAY, _QN = C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet)
+_FLT = C.POINTER(TtmpcFleet)
 SYMBOLS = {
     "ttmpc_default_config": (None, [_CFG]),
     "ttmpc_num_params": (_I, [_CFG]),
@@ -74,6 +91,9 @@ SYMBOLS = {
     "ttmpc_solve_batch_host": (_I, [_CFG, _I, _VP, _I, _I, _VP, _RES]),
     "ttmpc_eval_batch_device": (_I, [_CFG, _I] + [_VP] * 10),
     "ttmpc_eval_batch_host": (_I, [_CFG, _I] + [_VP] * 9),
+    "ttmpc_fleet_pack_device": (_I, [_CFG, _FLT, _VP, _VP]),
+    "ttmpc_fleet_advance_device": (_I, [_CFG, _FLT, _VP, _VP, _VP]),
+    "ttmpc_fleet_step_device": (_I, [_CFG, _FLT, _VP, _I, _RES, _VP]),
     "ttmpc_read_stats": (_I, [C.POINTER(C.c_ulonglong), _I]),
     "ttmpc_launch_info": (_I, [_CFG, _I] + [C.POINTER(C.c_int)] * 5),
     "ttmpc_measure_fp64_peak": (_I, [C.POINTER(_D), _VP]),

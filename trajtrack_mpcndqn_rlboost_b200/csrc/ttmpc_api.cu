@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -174,6 +175,16 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
                              int use_y0, const double *d_c0, const ttmpc_result *res,
                              cudaStream_t st, const int *d_ready);
 
+// warps per CTA of the split kernel: as many scene regions as fit the 227 KB of one SM (<= 12)
+static int split_warps(const DevCfg &g) {
+  const int w = (int)(232448 / (size_t)g.smem_per_warp);
+  return w > 12 ? 12 : w;
+}
+static bool use_split(const DevCfg &g) {
+  const char *e = std::getenv("TTMPC_SPLIT");
+  return e && e[0] == '1' && split_warps(g) >= 1;
+}
+
 extern "C" int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes, const double *d_p,
                                         int use_u0, int use_y0, const double *d_c0,
                                         const ttmpc_result *res, void *stream) {
@@ -197,7 +208,15 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   rc = grid_for(w, g, n_scenes, &grid);
   if (rc) return rc;
   const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
-  rc = ensure_dyn(w, (table ? table : 8) * (size_t)grid * g.warps_per_block);
+  DevCfg gs = g;  // split kernel: clusters of (solver CTA, evaluator CTA)
+  int clusters = 0;
+  if (use_split(g)) {
+    gs.warps_per_block = split_warps(g);
+    const long long want = ((long long)n_scenes + gs.warps_per_block - 1) / gs.warps_per_block;
+    clusters = (int)std::min<long long>(std::max(1, w->sm_count / 2), want);
+  }
+  rc = ensure_dyn(w, (table ? table : 8) * std::max((size_t)grid * g.warps_per_block,
+                                                    (size_t)clusters * gs.warps_per_block));
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
   const char *nh = std::getenv("TTMPC_NO_HELPERS");
@@ -211,8 +230,59 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   A.inner_iters = res->inner_iters; A.pred_states = res->pred_states; A.evals = res->evals;
   A.dyn_scratch = w->dyn_scratch; A.work_counter = w->work_counter; A.stats = w->stats;
   A.n_scenes = n_scenes; A.use_u0 = use_u0; A.use_y0 = use_y0;
-  CUDA_TRY(launch_solve(g, A, grid, st));
+  if (clusters > 0) CUDA_TRY(launch_solve_split(gs, A, clusters, st));
+  else CUDA_TRY(launch_solve(g, A, grid, st));
   return TTMPC_OK;
+}
+
+// ------------------------------------------------------------------ fleet step
+static int fleet_dims(const ttmpc_config *cfg, const ttmpc_fleet *f, FleetDims *d) {
+  DevCfg g;
+  int rc = make_devcfg(cfg, &g);
+  if (rc) return rc;
+  if (!f || f->n < 0) return fail(TTMPC_ERR_BAD_ARG, "fleet: null or n < 0");
+  if (f->n > 0 && (!f->state || !f->goal || !f->last_u || !f->idx_ref || !f->status || !f->ref_traj ||
+                   !f->ref_len || !f->stc))
+    return fail(TTMPC_ERR_BAD_ARG, "fleet: state, goal, last_u, idx_ref, status, ref_traj, ref_len, stc are required");
+  if (f->action_steps != 1) return fail(TTMPC_ERR_UNSUPPORTED, "fleet: only action_steps = 1 is supported");
+  if (f->ref_stride < 1) return fail(TTMPC_ERR_BAD_ARG, "fleet: ref_stride must be >= 1");
+  if (f->dyn_cur && (!f->dyn_last || !f->dyn_disp || f->n_dyn_live < 0 || f->n_dyn_live > cfg->Ndynobs))
+    return fail(TTMPC_ERR_BAD_ARG, "fleet: dyn_cur needs dyn_last, dyn_disp and 0 <= n_dyn_live <= Ndynobs");
+  d->N = cfg->N_hor; d->np = g.np; d->ts = cfg->ts;
+  d->n_other = cfg->ns * cfg->N_hor * cfg->Nother;
+  d->n_stc = cfg->Nstcobs * cfg->nstcobs;
+  d->n_dyn = cfg->Ndynobs * cfg->ndynobs * cfg->N_hor;
+  return TTMPC_OK;
+}
+extern "C" int ttmpc_fleet_pack_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet, double *d_p,
+                                       void *stream) {
+  FleetDims d;
+  int rc = fleet_dims(cfg, fleet, &d);
+  if (rc) return rc;
+  if (fleet->n == 0) return TTMPC_OK;
+  if (!d_p) return fail(TTMPC_ERR_BAD_ARG, "fleet: d_p is required");
+  CUDA_TRY(launch_fleet_pack(*fleet, d, d_p, (cudaStream_t)stream));
+  return TTMPC_OK;
+}
+extern "C" int ttmpc_fleet_advance_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet,
+                                          const double *d_u, const int *d_exit_status, void *stream) {
+  FleetDims d;
+  int rc = fleet_dims(cfg, fleet, &d);
+  if (rc) return rc;
+  if (fleet->n == 0) return TTMPC_OK;
+  if (!d_u) return fail(TTMPC_ERR_BAD_ARG, "fleet: d_u is required");
+  CUDA_TRY(launch_fleet_advance(*fleet, d, d_u, d_exit_status, (cudaStream_t)stream));
+  return TTMPC_OK;
+}
+extern "C" int ttmpc_fleet_step_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet, double *d_p,
+                                       int use_y0, const ttmpc_result *res, void *stream) {
+  if (!res || !res->u || !res->exit_status)
+    return fail(TTMPC_ERR_BAD_ARG, "fleet: res->u and res->exit_status are required");
+  int rc = ttmpc_fleet_pack_device(cfg, fleet, d_p, stream);
+  if (rc) return rc;
+  rc = ttmpc_solve_batch_device(cfg, fleet->n, d_p, 0, use_y0, nullptr, res, stream);
+  if (rc) return rc;
+  return ttmpc_fleet_advance_device(cfg, fleet, res->u, res->exit_status, stream);
 }
 
 // Cumulative device-side counters since the last reset:

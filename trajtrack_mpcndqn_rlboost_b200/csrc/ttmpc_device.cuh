@@ -192,8 +192,11 @@ struct WarpSmem {
   struct HelpHdr *hhdr;
 };
 struct HelpHdr {
+  unsigned long long bar;  // split kernel: mbarrier the peer CTA arrives on when a message is complete
   int state;        // 0 idle, 1 request posted, 2 result ready
   int grad;         // request: gradient wanted
+  int cmd, scene;   // split kernel: what the evaluator warp is asked to do / scene to stage
+  double *st_out;   // split kernel: predicted states of this evaluation go here (or null)
   double c, gamma_ls;
   double psi, f, f2sq, S, dd, g2;  // result
 };
@@ -228,7 +231,7 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, 
   b += sizeof(double) * (size_t)(mem + 1) * (mem + 1) * 2;
   b += sizeof(double) * ((mem + 2) / 2 * 2);
   b += sizeof(double) * (2 * (mem + 1));
-  b += sizeof(double2) * 3 * (size_t)N + 80;  // helper mailbox rows + header
+  b += sizeof(double2) * 3 * (size_t)N + (sizeof(HelpHdr) + 15) / 16 * 16;  // mailbox rows + header
   return (int)((b + 15) / 16 * 16);
 }
 

@@ -1,0 +1,147 @@
+// ttmpc_fleet.cu -- the caller side of the solve, batched on the device: one control step of
+// n independent robots as the reference's InterfaceMpc.get_action / TrajectoryGenerator.run_step
+// perform it (src/interface_mpc.py:72-92, src/mpc_traj_tracker/trajectory_generator.py:203-294).
+// See include/ttmpc.h ("Fleet step") for the contract; oracle/ttfleet_oracle.c is the CPU
+// restatement these kernels match bit for bit (use_libm = 0).
+//
+// Both kernels are copy / scalar work: pack writes the n x np parameter block once, coalesced
+// (HBM-bound, 21 KB per robot), advance touches 5 doubles per robot.
+#include <cuda_runtime.h>
+
+#include "ttmpc_device.cuh"
+#include "ttmpc_launch.cuh"
+
+namespace ttmpc {
+
+__device__ __forceinline__ double hyp2(double dx, double dy) { return sqrt(fma(dx, dx, dy * dy)); }
+
+// One CTA per robot.  Thread 0 does the scalar decisions (closest reference point, goal test,
+// speed reference); all threads then write the packed vector, element o of the row by thread
+// o mod blockDim (coalesced 8-byte stores).
+__global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, const FleetDims d,
+                                                         double *__restrict__ p_all) {
+  const int e = blockIdx.x;
+  if (e >= f.n) return;
+  __shared__ int s_idx;
+  __shared__ double s_speed;
+  const double *st = f.state + 3 * e, *goal = f.goal + 3 * e, *lu = f.last_u + 2 * e;
+  const double *ref = f.ref_traj + (size_t)e * f.ref_stride * 3;
+  const int L = f.ref_len[e], N = d.N;
+  if (threadIdx.x == 0) {
+    int idx = f.idx_ref[e];
+    const double x = st[0], y = st[1];
+    if (f.status[e] == TTMPC_FLEET_RUNNING) {
+      // get_local_ref_traj (trajectory_generator.py:214-219): first minimum in the window
+      int lo = idx - 1 * f.action_steps; if (lo < 0) lo = 0;
+      int hi = idx + 5 * f.action_steps; if (hi > L) hi = L;
+      double best = INFINITY; int arg = lo;
+      for (int i = lo; i < hi; i++) {
+        const double dist = hyp2(x - ref[3 * i], y - ref[3 * i + 1]);
+        if (dist < best) { best = dist; arg = i; }
+      }
+      idx = arg;
+      f.idx_ref[e] = idx;
+      // check_termination_condition (:158-164): np.allclose(atol=0.05, rtol=0) and |v| < 0.05
+      const bool close = fabs(x - goal[0]) <= 0.05 && fabs(y - goal[1]) <= 0.05;
+      if (close && fabs(lu[0]) < 0.05) f.status[e] = TTMPC_FLEET_REACHED;
+    }
+    s_idx = idx;
+    // speed reference (:248-255)
+    const double dist = hyp2(x - goal[0], y - goal[1]);
+    double v = f.base_speed;
+    if (!(dist >= f.base_speed * N * d.ts)) {
+      v = dist / N / d.ts;
+      if (!(v > f.low_speed)) v = f.low_speed;
+    }
+    s_speed = v;
+  }
+  __syncthreads();
+  const int idx = s_idx;
+  double *p = p_all + (size_t)e * d.np;
+  const int o_refs = 18, o_speed = o_refs + 3 * N, o_other = o_speed + N, o_stc = o_other + d.n_other,
+            o_dyn = o_stc + d.n_stc, o_ws = o_dyn + d.n_dyn, o_wd = o_ws + N;
+  const double *stc = f.stc + (f.stc_shared ? 0 : (size_t)e * d.n_stc);
+  for (int o = threadIdx.x; o < d.np; o += blockDim.x) {
+    double v;
+    if (o < 3) v = st[o];
+    else if (o < 6) { int r = idx + N - 1; if (r > L - 1) r = L - 1; v = ref[3 * r + (o - 3)]; }
+    else if (o < 8) v = lu[o - 6];
+    else if (o < o_refs) v = f.tuning[o - 8];
+    else if (o < o_speed) {
+      const int k = (o - o_refs) / 3, c = (o - o_refs) - 3 * k;
+      int r = idx + k; if (r > L - 1) r = L - 1;
+      v = ref[3 * r + c];
+    }
+    else if (o < o_other) v = s_speed;
+    else if (o < o_stc) v = f.other ? f.other[(size_t)e * d.n_other + (o - o_other)] : 0.0;
+    else if (o < o_dyn) v = stc[o - o_stc];
+    else if (o < o_ws) {
+      const int q = o - o_dyn;
+      if (f.dyn) v = f.dyn[(size_t)e * d.n_dyn + q];
+      else {
+        v = 0.0;
+        const int j = q / (6 * N);
+        if (f.dyn_cur && j < f.n_dyn_live) {  // est_dyn_obs_positions (main.py:80-89)
+          const int i = (q - j * 6 * N) / 6, c = q - j * 6 * N - 6 * i;
+          const double *cur = f.dyn_cur + ((size_t)e * f.n_dyn_live + j) * 2;
+          const double *last = f.dyn_last + ((size_t)e * f.n_dyn_live + j) * 2;
+          if (c < 2) v = cur[c] + (cur[c] - last[c]) * (double)(i + 1);
+          else if (c < 4) v = f.dyn_size;
+          else v = c == 4 ? 0.0 : 1.0;
+        }
+      }
+    }
+    else if (o < o_wd) v = f.stc_weight;
+    else v = f.dyn_weight;
+    p[o] = v;
+  }
+}
+
+// One thread per robot: obstacles move, RUNNING robots take the first control.
+__global__ void __launch_bounds__(128) fleet_advance_kernel(const ttmpc_fleet f, const FleetDims d,
+                                                            const double *__restrict__ u_all,
+                                                            const int *__restrict__ exit_status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= f.n) return;
+  if (f.dyn_cur) {
+    for (int j = 0; j < f.n_dyn_live; j++) {
+      double *c = f.dyn_cur + ((size_t)e * f.n_dyn_live + j) * 2;
+      double *l = f.dyn_last + ((size_t)e * f.n_dyn_live + j) * 2;
+      const double *dd = f.dyn_disp + ((size_t)e * f.n_dyn_live + j) * 2;
+      l[0] = c[0]; l[1] = c[1];
+      c[0] = c[0] + dd[0]; c[1] = c[1] + dd[1];
+    }
+  }
+  if (f.status[e] != TTMPC_FLEET_RUNNING) return;
+  if (exit_status && exit_status[e] == TTMPC_NOT_FINITE) { f.status[e] = TTMPC_FLEET_FAILED; return; }
+  const double *u = u_all + (size_t)e * 2 * d.N;
+  double *st = f.state + 3 * e;
+  const double v = u[0], w = u[1], ts = d.ts;
+  // unicycle_model, RK4 branch, in numpy's operation order (motion_model.py:166-174)
+  double s, c;
+  tt_sincos(st[2], &s, &c);
+  const double k1x = ts * (v * c), k1y = ts * (v * s), k1t = ts * w;
+  tt_sincos(st[2] + 0.5 * k1t, &s, &c);
+  const double k2x = ts * (v * c), k2y = ts * (v * s), k2t = ts * w;
+  tt_sincos(st[2] + 0.5 * k2t, &s, &c);
+  const double k3x = ts * (v * c), k3y = ts * (v * s), k3t = ts * w;
+  tt_sincos(st[2] + k3t, &s, &c);
+  const double k4x = ts * (v * c), k4y = ts * (v * s), k4t = ts * w;
+  const double sixth = 1.0 / 6.0;
+  st[0] = st[0] + sixth * (((k1x + 2.0 * k2x) + 2.0 * k3x) + k4x);
+  st[1] = st[1] + sixth * (((k1y + 2.0 * k2y) + 2.0 * k3y) + k4y);
+  st[2] = st[2] + sixth * (((k1t + 2.0 * k2t) + 2.0 * k3t) + k4t);
+  f.last_u[2 * e] = v; f.last_u[2 * e + 1] = w;
+}
+
+cudaError_t launch_fleet_pack(const ttmpc_fleet &f, const FleetDims &d, double *p, cudaStream_t st) {
+  fleet_pack_kernel<<<f.n, 128, 0, st>>>(f, d, p);
+  return cudaGetLastError();
+}
+cudaError_t launch_fleet_advance(const ttmpc_fleet &f, const FleetDims &d, const double *u,
+                                 const int *exit_status, cudaStream_t st) {
+  fleet_advance_kernel<<<(f.n + 127) / 128, 128, 0, st>>>(f, d, u, exit_status);
+  return cudaGetLastError();
+}
+
+}  // namespace ttmpc

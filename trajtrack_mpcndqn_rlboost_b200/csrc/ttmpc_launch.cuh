@@ -34,10 +34,16 @@ struct EvalArgs {
 };
 
 cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st);
+cudaError_t launch_solve_split(const DevCfg &g, const SolveArgs &A, int clusters, cudaStream_t st);
 cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream_t st);
 cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm);
 cudaError_t launch_probe(const DevCfg &g, const double *p, double *dyn, long long *out, int reps,
                          cudaStream_t st);
+// fleet step (ttmpc_fleet.cu)
+struct FleetDims { int N, np, n_other, n_stc, n_dyn; double ts; };
+cudaError_t launch_fleet_pack(const ttmpc_fleet &f, const FleetDims &d, double *p, cudaStream_t st);
+cudaError_t launch_fleet_advance(const ttmpc_fleet &f, const FleetDims &d, const double *u,
+                                 const int *exit_status, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t st);
 
 }  // namespace ttmpc

@@ -11,6 +11,7 @@
 // butterfly all-reduces.
 #include "ttmpc_device.cuh"
 #include "ttmpc_launch.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
 
@@ -223,36 +224,197 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define PROF_END(v, slot)
 #endif
 
+// ---------------------------------------------------------------- tail helpers
+// When the scene queue is empty, warps without work help the CTA-mates that still own a
+// long-running scene: the owner posts evaluation points into a mailbox, the helper evaluates
+// them on the owner's shared-memory tables.  The owner uses this to (a) overlap the Lipschitz
+// check psi(u_half) with the L-BFGS update/apply and (b) evaluate the next line-search
+// candidate speculatively.  Results never depend on whether a helper was there: speculative
+// work is discarded when the sequential algorithm would not have asked for it.
+struct CtaHelp {
+  int busy[8];    // warp w owns a live scene (tables staged)
+  int helper[8];  // helper[m] = warp helping owner m, or -1
+};
+struct HelpCtl {
+  bool enabled;              // helpers exist in this launch and have not timed out on this scene
+  volatile int *slot;        // &cta->helper[me]
+  bool pending;              // a posted request has not been collected yet
+  // split kernel (solver CTA): this warp's evaluator mailbox in the peer CTA's shared memory
+  double2 *r_hreq, *r_yrow;
+  HelpHdr *r_hdr;
+  unsigned phase, peer_rank; // parity of the next answer on sm.hhdr->bar; rank of the evaluator CTA
+  int *fail;                 // set when the evaluator did not answer (host re-runs the batch)
+};
+enum { CMD_EVAL = 0, CMD_STAGE = 1, CMD_EXIT = 2 };
+
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+// mbarrier helpers of the split kernel: a waiting warp sleeps in hardware instead of polling
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `peer_rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_peer(const void *local_bar, unsigned peer_rank) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(peer_rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, unsigned parity) {
+  unsigned ok;
+  const unsigned hint_ns = 100000;  // the warp may stay suspended this long before try_wait gives up
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+// false = nothing arrived within `limit_ns`
+__device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity, unsigned long long limit_ns) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  int n = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (((++n) & 63) == 0 && globaltimer_ns() - t0 > limit_ns) return false;
+  return true;
+}
+// SP = split kernel: requests go to the evaluator warp in the peer CTA (always there)
+template <bool SP>
+__device__ __forceinline__ bool help_available(const HelpCtl &hc) {
+  if constexpr (SP) return hc.enabled;
+  else return hc.enabled && *hc.slot >= 0;
+}
+template <bool SP>
+__device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int lane, int N, EvalOut &e);
+// The mailbox lives in the owner's shared-memory region (request row, answer row, header);
+// in the split kernel the request half is in the evaluator's region, the answer half here.
+template <bool SP>
+__device__ __forceinline__ void help_post(HelpCtl &hc, const WarpSmem &sm, int lane, int N, double v,
+                                          double w, double c, int grad, double gamma_ls,
+                                          int cmd = CMD_EVAL, int scene = 0, double *st_out = nullptr) {
+  if (hc.pending) {  // a speculative evaluation nobody needed: let it finish first
+    EvalOut tmp;
+    if (!help_wait<SP>(hc, sm, lane, N, tmp)) return;
+  }
+  if constexpr (SP) {
+    if (!hc.enabled) return;
+    // every lane stores its share of the message and then arrives (release) on the evaluator's
+    // barrier: no fence, no cross-lane ordering needed
+    if (lane < N) hc.r_hreq[lane] = make_double2(v, w);
+    {
+      HelpHdr *h = hc.r_hdr;
+      if (lane == 31) h->c = c;
+      if (lane == 30) h->gamma_ls = gamma_ls;
+      if (lane == 29) { h->grad = grad; h->cmd = cmd; }
+      if (lane == 28) h->scene = scene;
+      if (lane == 27) h->st_out = st_out;
+    }
+    mbar_arrive_peer(&sm.hhdr->bar, hc.peer_rank);
+  } else {
+    if (lane < N) sm.hreq[lane] = make_double2(v, w);
+    if (lane == 0) { sm.hhdr->c = c; sm.hhdr->gamma_ls = gamma_ls; sm.hhdr->grad = grad; }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 1;
+  }
+  hc.pending = true;
+}
+// Collect the posted evaluation.  false = the helper did not answer in time (treated as gone).
+template <bool SP>
+__device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int lane, int N, EvalOut &e) {
+  if (SP && !hc.pending) return false;
+  int ok = 1;
+  if constexpr (SP) {
+    ok = mbar_wait(&sm.hhdr->bar, hc.phase, 2000000000ull) ? 1 : 0;  // acquire, every lane
+    ok = __all_sync(FULL, ok);
+    hc.phase ^= 1u;
+  } else if (lane == 0) {
+    const volatile int *st = reinterpret_cast<volatile int *>(&sm.hhdr->state);
+    const unsigned long long t0 = globaltimer_ns();
+    int spins = 0;
+    while (*st != 2) {
+      if (((++spins) & 1023) == 0 && globaltimer_ns() - t0 > 50000000ull) { ok = 0; break; }
+    }
+  }
+  if (!SP) ok = __shfl_sync(FULL, ok, 0);
+  hc.pending = false;
+  if (!ok) {
+    hc.enabled = false;
+    if (SP && lane == 0 && hc.fail) atomicExch(hc.fail, 1);
+    return false;
+  }
+  if constexpr (!SP) __threadfence_block();
+  const volatile HelpHdr *h = sm.hhdr;
+  e.psi = h->psi; e.f = h->f; e.f2sq = h->f2sq; e.S = h->S; e.dd = h->dd; e.g2 = h->g2;
+  {
+    const volatile double *hr = reinterpret_cast<const volatile double *>(sm.hres);
+    e.gv = lane < N ? hr[2 * lane] : 0.0;
+    e.gw = lane < N ? hr[2 * lane + 1] : 0.0;
+  }
+  e.any_hard = false;
+  e.s0 = e.s1 = e.h0 = e.h1 = 0.0;
+  __syncwarp();
+  if (!SP && lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 0;
+  return true;
+}
+template <bool SP>
+__device__ __forceinline__ void help_drain(HelpCtl &hc, const WarpSmem &sm, int lane, int N) {
+  if (hc.pending) { EvalOut tmp; help_wait<SP>(hc, sm, lane, N, tmp); }
+}
+// split kernel: an evaluation is a request to the evaluator warp
+__device__ __forceinline__ EvalOut remote_eval(HelpCtl &hc, const WarpSmem &sm, int lane, int N, double v,
+                                               double w, double c, int grad, double gamma_ls,
+                                               double *st_out = nullptr) {
+  EvalOut e;
+  help_post<true>(hc, sm, lane, N, v, w, c, grad, gamma_ls, CMD_EVAL, 0, st_out);
+  if (!help_wait<true>(hc, sm, lane, N, e)) {
+    e.psi = e.f = e.f2sq = e.S = e.dd = e.g2 = e.gv = e.gw = NAN;
+    e.s0 = e.s1 = e.h0 = e.h1 = NAN; e.any_hard = false;
+  }
+  return e;
+}
+
 struct Problem {  // what eval needs besides the point
   double c, ya, yw;
 };
 
-template <class DM>
+template <class DM, bool SP>
 __device__ __forceinline__ double eval_cost(const DevCfg &g, const WarpSmem &sm, int lane,
-                                            const Problem &pb, double a0, double a1) {
-  PROF_BEGIN(t0)
-  EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                           pb.yw, nullptr, false, 0.0);
-  PROF_END(t0, 0)
+                                            const Problem &pb, double a0, double a1, HelpCtl &hc) {
+  if constexpr (SP) {
+    PROF_BEGIN(t0)
+    const EvalOut e = remote_eval(hc, sm, lane, DM::N(g), a0, a1, pb.c, 0, 0.0);
+    PROF_END(t0, 0)
+    if (lane == 0) sm.ctx->n_cost++;
+    return e.psi;
+  } else {
+    PROF_BEGIN(t0)
+    EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                             pb.yw, nullptr, false, 0.0);
+    PROF_END(t0, 0)
 #ifdef TTMPC_PROFILE_DOUBLE
-  {  // I-cache experiment: the same evaluation again, timed separately (slot 4)
-    PROF_BEGIN(t1)
-    EvalOut e2 = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                              pb.yw, nullptr, false, 0.0);
-    PROF_END(t1, 4)
-    if (e2.psi != e.psi) __trap();
-  }
+    {  // I-cache experiment: the same evaluation again, timed separately (slot 4)
+      PROF_BEGIN(t1)
+      EvalOut e2 = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
+                                pb.yw, nullptr, false, 0.0);
+      PROF_END(t1, 4)
+      if (e2.psi != e.psi) __trap();
+    }
 #endif
-  if (lane == 0) sm.ctx->n_cost++;
-  return e.psi;
+    if (lane == 0) sm.ctx->n_cost++;
+    return e.psi;
+  }
 }
-template <class DM>
+template <class DM, bool SP>
 __device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm, int lane,
                                             const Problem &pb, double a0, double a1, double &o0,
-                                            double &o1) {
+                                            double &o1, HelpCtl &hc) {
   PROF_BEGIN(t0)
-  EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya,
-                           pb.yw, nullptr, true, 0.0);
+  EvalOut e;
+  if constexpr (SP) {
+    e = remote_eval(hc, sm, lane, DM::N(g), a0, a1, pb.c, 1, 0.0);
+  } else {
+    e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), a0, a1, pb.c, pb.ya, pb.yw,
+                     nullptr, true, 0.0);
+  }
   PROF_END(t0, 1)
   if (lane == 0) sm.ctx->n_grad++;
   o0 = e.gv; o1 = e.gw;
@@ -271,73 +433,6 @@ __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z,
                                                        double a0, double a1) {
   z.s0 = fma(-U.gamma, z.g0, a0); z.s1 = fma(-U.gamma, z.g1, a1);
   project(g, z.s0, z.s1, z.h0, z.h1);
-}
-
-// ---------------------------------------------------------------- tail helpers
-// When the scene queue is empty, warps without work help the CTA-mates that still own a
-// long-running scene: the owner posts evaluation points into a mailbox, the helper evaluates
-// them on the owner's shared-memory tables.  The owner uses this to (a) overlap the Lipschitz
-// check psi(u_half) with the L-BFGS update/apply and (b) evaluate the next line-search
-// candidate speculatively.  Results never depend on whether a helper was there: speculative
-// work is discarded when the sequential algorithm would not have asked for it.
-struct CtaHelp {
-  int busy[8];    // warp w owns a live scene (tables staged)
-  int helper[8];  // helper[m] = warp helping owner m, or -1
-};
-struct HelpCtl {
-  bool enabled;              // helpers exist in this launch and have not timed out on this scene
-  volatile int *slot;        // &cta->helper[me]
-  bool pending;              // a posted request has not been collected yet
-};
-
-__device__ __forceinline__ bool help_available(const HelpCtl &hc) {
-  return hc.enabled && *hc.slot >= 0;
-}
-__device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int lane, int N, EvalOut &e);
-// The mailbox lives in the owner's shared-memory region (request row, answer row, header).
-__device__ __forceinline__ void help_post(HelpCtl &hc, const WarpSmem &sm, int lane, int N, double v,
-                                          double w, double c, int grad, double gamma_ls) {
-  if (hc.pending) {  // a speculative evaluation nobody needed: let it finish first
-    EvalOut tmp;
-    if (!help_wait(hc, sm, lane, N, tmp)) return;
-  }
-  if (lane < N) sm.hreq[lane] = make_double2(v, w);
-  if (lane == 0) { sm.hhdr->c = c; sm.hhdr->gamma_ls = gamma_ls; sm.hhdr->grad = grad; }
-  __threadfence_block();
-  __syncwarp();
-  if (lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 1;
-  hc.pending = true;
-}
-// Collect the posted evaluation.  false = the helper did not answer in time (treated as gone).
-__device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int lane, int N, EvalOut &e) {
-  int ok = 1;
-  if (lane == 0) {
-    const volatile int *st = reinterpret_cast<volatile int *>(&sm.hhdr->state);
-    const unsigned long long t0 = globaltimer_ns();
-    int spins = 0;
-    while (*st != 2) {
-      if (((++spins) & 1023) == 0 && globaltimer_ns() - t0 > 50000000ull) { ok = 0; break; }
-    }
-  }
-  ok = __shfl_sync(FULL, ok, 0);
-  hc.pending = false;
-  if (!ok) { hc.enabled = false; return false; }
-  __threadfence_block();
-  const volatile HelpHdr *h = sm.hhdr;
-  e.psi = h->psi; e.f = h->f; e.f2sq = h->f2sq; e.S = h->S; e.dd = h->dd; e.g2 = h->g2;
-  {
-    const volatile double *hr = reinterpret_cast<const volatile double *>(sm.hres);
-    e.gv = lane < N ? hr[2 * lane] : 0.0;
-    e.gw = lane < N ? hr[2 * lane + 1] : 0.0;
-  }
-  e.any_hard = false;
-  e.s0 = e.s1 = e.h0 = e.h1 = 0.0;
-  __syncwarp();
-  if (lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 0;
-  return true;
-}
-__device__ __forceinline__ void help_drain(HelpCtl &hc, const WarpSmem &sm, int lane, int N) {
-  if (hc.pending) { EvalOut tmp; help_wait(hc, sm, lane, N, tmp); }
 }
 
 // A warp that ran out of scenes serves its CTA-mates until none of them owns a scene.
@@ -413,7 +508,7 @@ __device__ void helper_loop(const DevCfg &g, const SolveArgs &A, CtaHelp *cta, u
 }
 
 // PANOCEngine::step.  Returns true to continue.
-template <class DM>
+template <class DM, bool SP>
 __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, int lane, const Problem &pb,
                            Lane &z, Uni &U, double tolerance, HelpCtl &hc) {
   if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
@@ -429,18 +524,18 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   bool lbfgs_done = false;
   {
     double cost_half;
-    if (__builtin_expect(help_available(hc), 0)) {
-      help_post(hc, sm, lane, DM::N(g), z.h0, z.h1, pb.c, 0, 0.0);
+    if (__builtin_expect(help_available<SP>(hc), SP ? 1 : 0)) {
+      help_post<SP>(hc, sm, lane, DM::N(g), z.h0, z.h1, pb.c, 0, 0.0);
       const int s_first = U.lb_first, s_head = U.lb_head, s_active = U.lb_active;
       const double s_gamma = U.lb_gamma, s_os0 = z.os0, s_os1 = z.os1, s_og0 = z.og0, s_og1 = z.og1;
       lbfgs_update<DM>(g, sm, z, U, lane);
       if (U.iteration > 0) { z.d0 = z.f0; z.d1 = z.f1; lbfgs_apply<DM>(g, sm, z, U, lane); }
       EvalOut r;
-      if (hc.pending && help_wait(hc, sm, lane, DM::N(g), r)) {
+      if (hc.pending && help_wait<SP>(hc, sm, lane, DM::N(g), r)) {
         cost_half = r.psi;
         if (lane == 0) sm.ctx->n_cost++;
       } else {
-        cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
+        cost_half = eval_cost<DM, SP>(g, sm, lane, pb, z.h0, z.h1, hc);
       }
       const double rhs0 = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
                           (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
@@ -451,7 +546,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         lbfgs_done = true;
       }
     } else {
-      cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
+      cost_half = eval_cost<DM, SP>(g, sm, lane, pb, z.h0, z.h1, hc);
     }
     int it = 0;
     while (true) {
@@ -465,7 +560,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       U.L *= 2.0;
       U.gamma /= 2.0;
       gradient_and_half_step(g, z, U, z.u0, z.u1);
-      cost_half = eval_cost<DM>(g, sm, lane, pb, z.h0, z.h1);
+      cost_half = eval_cost<DM, SP>(g, sm, lane, pb, z.h0, z.h1, hc);
       compute_fpr(z, U);
       it++;
     }
@@ -488,7 +583,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   if (U.iteration == 0) {
     // update_no_linesearch
     z.u0 = z.h0; z.u1 = z.h1;
-    U.cost = eval_grad<DM>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
+    U.cost = eval_grad<DM, SP>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1, hc);
     gradient_and_half_step(g, z, U, z.u0, z.u1);
     U.env_valid = 0;
   } else {
@@ -511,14 +606,30 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       const double one_m = 1.0 - U.tau;
       p0 = fma(-U.tau, z.d0, fma(-one_m, z.f0, z.u0));
       p1 = fma(-U.tau, z.d1, fma(-one_m, z.f1, z.u1));
+      if constexpr (SP) {
+        // split kernel: the evaluation runs on the evaluator warp; the gradient step and the
+        // half step are formed here from the returned gradient (same operations)
+        PROF_BEGIN(t0)
+        const EvalOut e = remote_eval(hc, sm, lane, DM::N(g), p0, p1, pb.c, 1, U.gamma);
+        PROF_END(t0, 1)
+        if (lane == 0) sm.ctx->n_grad++;
+        U.cost = e.psi;
+        z.g0 = e.gv; z.g1 = e.gw;
+        gradient_and_half_step(g, z, U, p0, p1);
+        const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+        U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
+        if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
+        U.tau /= 2.0;
+        nls++;
+      } else {
       // with a helper: the next candidate (tau/2) is evaluated speculatively at the same time
       bool posted = false;
       double n0 = 0.0, n1 = 0.0;
-      if (__builtin_expect(nls < MAX_LINESEARCH_ITERATIONS && help_available(hc), 0)) {
+      if (__builtin_expect(nls < MAX_LINESEARCH_ITERATIONS && help_available<SP>(hc), 0)) {
         const double tau2 = U.tau / 2.0, one_m2 = 1.0 - tau2;
         n0 = fma(-tau2, z.d0, fma(-one_m2, z.f0, z.u0));
         n1 = fma(-tau2, z.d1, fma(-one_m2, z.f1, z.u1));
-        help_post(hc, sm, lane, DM::N(g), n0, n1, pb.c, 1, U.gamma);
+        help_post<SP>(hc, sm, lane, DM::N(g), n0, n1, pb.c, 1, U.gamma);
         posted = hc.pending;
       }
       // cost, gradient, gradient step, half step and both envelope scalars in one evaluation
@@ -534,7 +645,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
       U.tau /= 2.0;
       nls++;
-      if (posted && help_wait(hc, sm, lane, DM::N(g), e)) {  // the helper's evaluation is the one at this tau
+      if (posted && help_wait<SP>(hc, sm, lane, DM::N(g), e)) {  // the helper's evaluation is the one at this tau
         if (lane == 0) sm.ctx->n_grad++;
         p0 = n0; p1 = n1;
         U.cost = e.psi;
@@ -545,6 +656,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
         U.tau /= 2.0;
         nls++;
+      }
       }
     }
     z.u0 = p0; z.u1 = p1;
@@ -559,7 +671,7 @@ __device__ __forceinline__ void panoc_reset(Uni &U) {
 }
 
 // One scene, start to finish.
-template <class DM>
+template <class DM, bool SP>
 __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs &A, int scene,
                             int lane, unsigned long long *wstats, HelpCtl &hc) {
   const int N = g.N;
@@ -601,15 +713,15 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     num_outer++;
     pb.ya = clipd(pb.ya, -1e12, 1e12);
     pb.yw = clipd(pb.yw, -1e12, 1e12);
-    help_drain(hc, sm, lane, N);
-    if (act) sm.yrow[lane] = make_double2(pb.ya, pb.yw);  // what a helper evaluates with
+    help_drain<SP>(hc, sm, lane, N);
+    if (act) (SP ? hc.r_yrow : sm.yrow)[lane] = make_double2(pb.ya, pb.yw);  // what a helper evaluates with
     __syncwarp();
     // ---------------- inner problem: PANOCOptimizer::solve
     int inner_status;
     {
       panoc_reset(U);
       // init: cost, gradient, local Lipschitz estimate
-      U.cost = eval_grad<DM>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1);
+      U.cost = eval_grad<DM, SP>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1, hc);
       if (lane == 0) sm.ctx->n_cost++;  // the reference evaluates cost and gradient separately
       {
         double h0 = 0.0, h1 = 0.0;
@@ -618,7 +730,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
           h1 = (EPSILON_LIPSCHITZ * z.u1 > DELTA_LIPSCHITZ) ? EPSILON_LIPSCHITZ * z.u1 : DELTA_LIPSCHITZ;
         }
         double t0, t1;
-        eval_grad<DM>(g, sm, lane, pb, z.u0 + h0, z.u1 + h1, t0, t1);
+        eval_grad<DM, SP>(g, sm, lane, pb, z.u0 + h0, z.u1 + h1, t0, t1, hc);
         const double e0 = t0 - z.g0, e1 = t1 - z.g1;
         double nh = pdot(h0, h1, h0, h1);
         double nd = pdot(e0, e1, e0, e1);
@@ -634,7 +746,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
       int num_iter = 0;
       bool cont = true;
       while (true) {
-        const bool flag = panoc_step<DM>(g, sm, lane, pb, z, U, g.tol, hc);
+        const bool flag = panoc_step<DM, SP>(g, sm, lane, pb, z, U, g.tol, hc);
         if (!(flag && cont)) break;
         num_iter++;
         cont = num_iter < g.max_inner;
@@ -663,8 +775,10 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
       if (!act) { yp_a = 0.0; yp_w = 0.0; }
     }
     {
-      EvalOut e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0,
-                               0.0, nullptr, false, 0.0);
+      EvalOut e;
+      if constexpr (SP) e = remote_eval(hc, sm, lane, N, z.u0, z.u1, 0.0, 0, 0.0);  // c = 0: the multipliers do not enter f, F2
+      else e = eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0,
+                            0.0, nullptr, false, 0.0);
       if (lane == 0) sm.ctx->n_cost++;
       f2_norm_plus = sqrt(e.f2sq);
       f_final = e.f;
@@ -692,7 +806,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
   if (exit_status != TTMPC_NOT_FINITE && num_outer == g.max_outer)
     exit_status = TTMPC_NOT_CONVERGED_ITERATIONS;
 
-  help_drain(hc, sm, lane, N);  // no evaluation on this scene's tables may still be in flight
+  help_drain<SP>(hc, sm, lane, N);  // no evaluation on this scene's tables may still be in flight
   // ---------------- results
   if (act) {
     A.u[(size_t)scene * 2 * N + 2 * lane] = z.u0;
@@ -703,8 +817,9 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     }
   }
   if (A.pred_states) {
-    eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0, 0.0,
-                 A.pred_states + (size_t)scene * N * 3, false, 0.0);
+    if constexpr (SP) remote_eval(hc, sm, lane, N, z.u0, z.u1, 0.0, 0, 0.0, A.pred_states + (size_t)scene * N * 3);
+    else eval_psi<DM>(&g, reinterpret_cast<unsigned char *>(sm.ctx), z.u0, z.u1, 0.0, 0.0, 0.0,
+                      A.pred_states + (size_t)scene * N * 3, false, 0.0);
   }
   if (lane == 0) {
     if (A.cost) A.cost[scene] = f_final;
@@ -753,6 +868,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
   hc.enabled = A.helpers != 0;
   hc.slot = &cta->helper[warp];
   hc.pending = false;
+  hc.r_hreq = nullptr; hc.r_yrow = nullptr; hc.r_hdr = nullptr; hc.fail = nullptr; hc.phase = 0; hc.peer_rank = 0;
   if (lane == 0) sm.hhdr->state = 0;
   unsigned long long wstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   while (true) {
@@ -779,7 +895,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
     stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
     if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 1;
     hc.enabled = A.helpers != 0;
-    solve_scene<DM>(g, sm, A, scene, lane, wstats, hc);
+    solve_scene<DM, false>(g, sm, A, scene, lane, wstats, hc);
     if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 0;
     __syncwarp();
   }
@@ -789,6 +905,150 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
     for (int i = 0; i < 8; i++)
       if (wstats[i]) atomicAdd(A.stats + i, wstats[i]);
   }
+}
+
+
+// ------------------------------------------------------------------ split kernel
+// The hot loop of solve_kernel is ~47 KB of SASS per PANOC iteration against a 32 KB
+// instruction cache: with all resident warps at different places in it the SM is bound by
+// instruction-cache refills (a warp runs 3x slower than alone; the same code run in phase by
+// all warps only 1.3x, see tools/probe.py).  Here a cluster of two CTAs splits the work by
+// CODE: the solver CTA (rank 0) runs PANOC / L-BFGS / ALM and owns the L-BFGS history, the
+// evaluator CTA (rank 1) holds the scene tables and runs stage_scene + eval_psi.  Warp w of
+// the solver is paired with warp w of the evaluator; they talk through mailboxes in each
+// other's shared memory (DSMEM, ~215 cycles): request row + header in the evaluator's region,
+// gradient row + header in the solver's.  Each SM now loops over < 32 KB of code.  The
+// Lipschitz check psi(u_half) overlaps with the L-BFGS update/apply on every iteration
+// (the speculative path the tail helpers use).  Arithmetic is unchanged: results are
+// bit-identical to solve_kernel.
+template <class DM>
+__device__ void evaluator_loop(const DevCfg &g, const SolveArgs &A, unsigned char *my_base,
+                               const WarpSmem &peer, double *dyn, int lane, unsigned long long *wstats) {
+  const WarpSmem mine = carve<DM>(my_base, g);
+  const int N = g.N;
+  bool staged = false;
+  unsigned phase = 0;
+  const unsigned solver_rank = 0;
+  while (true) {
+    // sleep on the mailbox barrier until the solver warp has posted a message
+    if (!__all_sync(FULL, mbar_wait(&mine.hhdr->bar, phase, 5000000000ull))) break;  // never hang the GPU
+    phase ^= 1u;
+    const volatile HelpHdr *h = mine.hhdr;
+    const int cmd = h->cmd, scene = h->scene, grad = h->grad;
+    const double c = h->c, gamma_ls = h->gamma_ls;
+    double *st_out = h->st_out;
+    double2 pt = make_double2(0.0, 0.0), yv = make_double2(0.0, 0.0);
+    if (lane < N) {
+      const volatile double *rq = reinterpret_cast<const volatile double *>(mine.hreq);
+      const volatile double *yr = reinterpret_cast<const volatile double *>(mine.yrow);
+      pt.x = rq[2 * lane]; pt.y = rq[2 * lane + 1];
+      yv.x = yr[2 * lane]; yv.y = yr[2 * lane + 1];
+    }
+    __syncwarp();
+    if (cmd == CMD_EXIT) break;
+    if (cmd == CMD_STAGE) {
+      if (staged) wstats[2] += mine.ctx->n_body;
+      __syncwarp();
+      stage_scene(g, mine, A.p + (size_t)scene * g.np, dyn, lane);
+      staged = true;
+    } else {
+#ifdef TTMPC_PROFILE
+      const long long tp0 = clock64();
+#endif
+      const EvalOut e = eval_psi<DM>(&g, my_base, pt.x, pt.y, c, yv.x, yv.y, st_out, grad != 0, gamma_ls);
+#ifdef TTMPC_PROFILE
+      wstats[6] += clock64() - tp0;  // evaluator-side cycles (reported in the L-BFGS slot)
+#endif
+      if (lane < N) peer.hres[lane] = make_double2(e.gv, e.gw);
+      {
+        HelpHdr *r = peer.hhdr;
+        if (lane == 31) r->psi = e.psi;
+        if (lane == 30) r->f = e.f;
+        if (lane == 29) r->f2sq = e.f2sq;
+        if (lane == 28) r->S = e.S;
+        if (lane == 27) r->dd = e.dd;
+        if (lane == 26) r->g2 = e.g2;
+      }
+    }
+    mbar_arrive_peer(&mine.hhdr->bar, solver_rank);  // every lane: its stores, then release-arrive
+  }
+  if (staged) wstats[2] += mine.ctx->n_body;
+}
+
+template <class DM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+    solve_split_kernel(const __grid_constant__ DevCfg g, const __grid_constant__ SolveArgs A) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster.block_rank();
+  unsigned char *my_base = smem_raw + (size_t)warp * g.smem_per_warp;
+  const WarpSmem sm = carve<DM>(my_base, g);
+  const WarpSmem peer = carve<DM>(cluster.map_shared_rank(my_base, rank ^ 1u), g);
+  if (lane == 0) {
+    sm.hhdr->state = 0;
+    mbar_init(&sm.hhdr->bar, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();
+  unsigned long long wstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rank == 0) {
+    HelpCtl hc;
+    hc.enabled = true; hc.slot = nullptr; hc.pending = false; hc.phase = 0; hc.peer_rank = 1;
+    hc.r_hreq = peer.hreq; hc.r_yrow = peer.yrow; hc.r_hdr = peer.hhdr; hc.fail = A.timeout_flag;
+    const int N = g.N;
+    while (true) {
+      int scene = 0;
+      if (lane == 0) scene = atomicAdd(A.work_counter, 1);
+      scene = __shfl_sync(FULL, scene, 0);
+      if (scene >= A.n_scenes) break;
+      if (A.ready) {  // parameters of this scene may still be on their way from the host
+        int ok = 1;
+        if (lane == 0) {
+          const volatile int *rdy = A.ready;
+          const unsigned long long t0 = globaltimer_ns();
+          while (*rdy <= scene) {
+            __nanosleep(200);
+            if (globaltimer_ns() - t0 > 2000000000ull) {
+              ok = 0; if (A.timeout_flag) atomicExch(A.timeout_flag, 1); break;
+            }
+          }
+        }
+        ok = __shfl_sync(FULL, ok, 0);
+        if (!ok) break;
+        __threadfence();
+      }
+      // the evaluator builds the scene tables; this side only needs the initial controls
+      help_post<true>(hc, sm, lane, N, 0.0, 0.0, 0.0, 0, 0.0, CMD_STAGE, scene, nullptr);
+      if (lane == 0) {
+        const double *s = A.p + (size_t)scene * g.np + g.off_s;
+        WarpCtx *c = sm.ctx;
+        c->v_init = s[6]; c->w_init = s[7];
+        c->n_cost = 0; c->n_grad = 0; c->n_body = 0;
+#ifdef TTMPC_PROFILE
+        for (int i = 0; i < 8; i++) c->prof[i] = 0;
+        for (int i = 0; i < 10; i++) c->eprof[i] = 0;
+#endif
+      }
+      __syncwarp();
+      { EvalOut ack; help_wait<true>(hc, sm, lane, N, ack); }
+      solve_scene<DM, true>(g, sm, A, scene, lane, wstats, hc);
+      __syncwarp();
+    }
+    hc.enabled = true;  // the evaluator warp must always be released
+    help_drain<true>(hc, sm, lane, N);
+    help_post<true>(hc, sm, lane, N, 0.0, 0.0, 0.0, 0, 0.0, CMD_EXIT, 0, nullptr);
+  } else {
+    const int W = blockDim.x >> 5;
+    double *dyn = A.dyn_scratch + ((size_t)(blockIdx.x >> 1) * W + warp) * DYN_FIELDS * g.Ndyn * g.N;
+    evaluator_loop<DM>(g, A, my_base, peer, dyn, lane, wstats);
+  }
+  if (lane == 0 && A.stats) {
+    for (int i = 0; i < 8; i++)
+      if (wstats[i]) atomicAdd(A.stats + i, wstats[i]);
+  }
+  cluster.sync();  // nobody leaves while its shared memory may still be written by the peer
 }
 
 // ------------------------------------------------------------------ batched evaluation
@@ -931,6 +1191,19 @@ cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStre
   } else {
     if ((e = set_smem(solve_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
     solve_kernel<DimsRuntime><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+  }
+  return cudaGetLastError();
+}
+// clusters of (solver CTA, evaluator CTA); g.warps_per_block warps each
+cudaError_t launch_solve_split(const DevCfg &g, const SolveArgs &A, int clusters, cudaStream_t st) {
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;
+  cudaError_t e;
+  if (is_default_dims(g)) {
+    if ((e = set_smem(solve_split_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
+    solve_split_kernel<DimsDefault><<<2 * clusters, g.warps_per_block * 32, smem, st>>>(g, A);
+  } else {
+    if ((e = set_smem(solve_split_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
+    solve_split_kernel<DimsRuntime><<<2 * clusters, g.warps_per_block * 32, smem, st>>>(g, A);
   }
   return cudaGetLastError();
 }

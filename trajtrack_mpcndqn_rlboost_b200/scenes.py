@@ -128,3 +128,36 @@ WORKLOADS = {
     "dynamic8192": dict(n=8192, n_static=3, n_dynamic=4, blocking_fraction=0.1,
                         solver=dict(max_inner_iterations=2000, max_outer_iterations=20)),
 }
+
+
+def make_fleet(n: int, seed: int = 0, n_static: int = 4, n_moving: int = 2):
+    """Synthetic closed-loop fleet for FleetPlanner: every robot gets a start pose, a three-node
+    reference path (10-20 m), its own rectangles near the path and obstacles crossing it at
+    constant velocity.  Returns a dict of numpy arrays / lists."""
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(8.0, 32.0, n); y0 = rng.uniform(8.0, 32.0, n)
+    heading = rng.uniform(-np.pi, np.pi, n)
+    leg1 = rng.uniform(4.0, 9.0, n); leg2 = rng.uniform(4.0, 9.0, n)
+    h2 = heading + rng.uniform(-0.9, 0.9, n)
+    mx, my = x0 + leg1 * np.cos(heading), y0 + leg1 * np.sin(heading)
+    gx, gy = mx + leg2 * np.cos(h2), my + leg2 * np.sin(h2)
+    lateral = rng.normal(0.0, 0.1, n)
+    init = np.stack([x0 - lateral * np.sin(heading), y0 + lateral * np.cos(heading),
+                     heading + rng.normal(0.0, 0.2, n)], axis=1)
+    goal = np.stack([gx, gy, np.zeros(n)], axis=1)
+    paths = [[(x0[i], y0[i]), (mx[i], my[i]), (gx[i], gy[i])] for i in range(n)]
+    along = rng.uniform(2.0, 8.0, (n, n_static))
+    side = rng.choice([-1.0, 1.0], (n, n_static)) * rng.uniform(1.3, 3.0, (n, n_static))
+    cx = x0[:, None] + along * np.cos(heading)[:, None] - side * np.sin(heading)[:, None]
+    cy = y0[:, None] + along * np.sin(heading)[:, None] + side * np.cos(heading)[:, None]
+    hx = rng.uniform(0.3, 0.9, (n, n_static)); hy = rng.uniform(0.3, 0.9, (n, n_static))
+    polys = [[[(cx[i, j] - hx[i, j], cy[i, j] - hy[i, j]), (cx[i, j] + hx[i, j], cy[i, j] - hy[i, j]),
+               (cx[i, j] + hx[i, j], cy[i, j] + hy[i, j]), (cx[i, j] - hx[i, j], cy[i, j] + hy[i, j])]
+              for j in range(n_static)] for i in range(n)]
+    a = rng.uniform(3.0, 9.0, (n, n_moving)); s = rng.choice([-1.0, 1.0], (n, n_moving)) * rng.uniform(3.0, 5.0, (n, n_moving))
+    ox = x0[:, None] + a * np.cos(heading)[:, None] - s * np.sin(heading)[:, None]
+    oy = y0[:, None] + a * np.sin(heading)[:, None] + s * np.cos(heading)[:, None]
+    vdir = rng.uniform(-np.pi, np.pi, (n, n_moving)); vmag = rng.uniform(0.0, 0.05, (n, n_moving))
+    return dict(init=init, goal=goal, paths=paths, static_polys=polys,
+                moving_pos=np.stack([ox, oy], axis=-1),
+                moving_disp=np.stack([vmag * np.cos(vdir), vmag * np.sin(vdir)], axis=-1))
