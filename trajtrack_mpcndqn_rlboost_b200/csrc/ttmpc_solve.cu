@@ -876,6 +876,9 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
     if (lane == 0) scene = atomicAdd(A.work_counter, 1);
     scene = __shfl_sync(FULL, scene, 0);
     if (scene >= A.n_scenes) break;
+    // owner from here on: warps that find the queue empty may attach as helpers already while
+    // the tables are being staged (requests are only posted from solve_scene)
+    if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 1;
     if (A.ready) {  // parameters of this scene may still be on their way from the host
       int ok = 1;
       if (lane == 0) {
@@ -889,11 +892,13 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
         }
       }
       ok = __shfl_sync(FULL, ok, 0);
-      if (!ok) break;
+      if (!ok) {
+        if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 0;
+        break;
+      }
       __threadfence();
     }
     stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
-    if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 1;
     hc.enabled = A.helpers != 0;
     solve_scene<DM, false>(g, sm, A, scene, lane, wstats, hc);
     if (lane == 0) *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 0;
