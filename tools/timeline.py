@@ -7,7 +7,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "static4096"
 w = t.scenes.WORKLOADS[name]
 cfg = t.Configurator().to_ttmpc(**w["solver"])
 n_over = int(sys.argv[2]) if len(sys.argv) > 2 else w["n"]
-p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
+p = t.scenes.make_scenes(max(w["n"], n_over), cfg, seed=1000, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
                          blocking_fraction=w["blocking_fraction"])[:n_over]
 s = t.BatchSolver(cfg)
 dp = torch.from_numpy(p).cuda(); bufs = s.alloc_device(len(p))
@@ -23,3 +23,7 @@ order = np.argsort(-dur)[:8]
 print("slowest:", [(int(i), round(float(dur[i]), 2), int(n_ev[i]), round(float(start[i]), 2)) for i in order])
 slots = s.launch_info(len(p))["grid"] * 4
 print("warp slots", slots, "ideal balanced ms", dur.sum() / slots)
+fin = start + dur
+late = np.argsort(-fin)[:8]
+print("last to finish:", [(int(i), "start %.1f" % start[i], "dur %.1f" % dur[i], int(n_ev[i])) for i in late])
+print("scenes still running at 70/80/90%% of the kernel: %s" % [int(((start < f * fin.max()) & (fin > f * fin.max())).sum()) for f in (0.7, 0.8, 0.9)])

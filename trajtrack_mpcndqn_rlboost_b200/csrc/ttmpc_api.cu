@@ -105,6 +105,7 @@ struct Workspace {
   cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
   cudaEvent_t ev_inputs = nullptr;
   unsigned long long *stats = nullptr;
+  int *order = nullptr; size_t order_ints = 0;  // dispatch order + ranking scratch
   // device staging for the host API
   void *dbuf = nullptr; size_t dbytes = 0;
   void *hbuf = nullptr; size_t hbytes = 0;
@@ -139,6 +140,14 @@ static int ensure_dyn(Workspace *w, size_t bytes) {
   w->dyn_scratch = nullptr; w->dyn_bytes = 0;
   CUDA_TRY(cudaMalloc(&w->dyn_scratch, bytes));
   w->dyn_bytes = bytes;
+  return TTMPC_OK;
+}
+static int ensure_order(Workspace *w, size_t ints) {
+  if (ints <= w->order_ints) return TTMPC_OK;
+  if (w->order) CUDA_TRY(cudaFree(w->order));
+  w->order = nullptr; w->order_ints = 0;
+  CUDA_TRY(cudaMalloc(&w->order, ints * sizeof(int)));
+  w->order_ints = ints;
   return TTMPC_OK;
 }
 static int ensure_staging(Workspace *w, size_t bytes) {
@@ -229,7 +238,23 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   A.penalty = res->penalty; A.exit_status = res->exit_status; A.outer_iters = res->outer_iters;
   A.inner_iters = res->inner_iters; A.pred_states = res->pred_states; A.evals = res->evals;
   A.dyn_scratch = w->dyn_scratch; A.work_counter = w->work_counter; A.stats = w->stats;
+  A.run_stats = w->stats + 18;  // stats block: [18] evaluations, [19] count of finished scenes
+  { const char *ne = std::getenv("TTMPC_NO_EARLY_HELP"); if (ne && ne[0] == '1') A.run_stats = nullptr; }
   A.n_scenes = n_scenes; A.use_u0 = use_u0; A.use_y0 = use_y0;
+  // more scenes than resident warps: dispatch the likely-long ones first.  Not on the streamed
+  // host path (scenes become available in index order there).  TTMPC_NO_ORDER=1 disables it.
+  A.order = nullptr;
+  {
+    const char *no = std::getenv("TTMPC_NO_ORDER");
+    const long long resident = clusters > 0 ? (long long)clusters * gs.warps_per_block
+                                            : (long long)grid * g.warps_per_block;
+    if (!d_ready && n_scenes > resident && !(no && no[0] == '1')) {
+      rc = ensure_order(w, 2 * (size_t)n_scenes + 64);
+      if (rc) return rc;
+      CUDA_TRY(launch_rank_scenes(g, d_p, n_scenes, w->order + n_scenes, w->order, st));
+      A.order = w->order;
+    }
+  }
   if (clusters > 0) CUDA_TRY(launch_solve_split(gs, A, clusters, st));
   else CUDA_TRY(launch_solve(g, A, grid, st));
   return TTMPC_OK;

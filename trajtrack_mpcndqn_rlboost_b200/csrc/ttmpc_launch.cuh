@@ -16,12 +16,14 @@ struct SolveArgs {
   long long *evals;     // [n][4] or null
   double *dyn_scratch;  // [total_warps][DYN_FIELDS*Ndyn*N]
   int *work_counter;    // dynamic scene queue
+  const int *order;     // optional dispatch order (likely-long scenes first) or null
   unsigned long long *eprof;  // [10] eval section cycles (diagnostic build) or null
   int helpers;          // 1: warps that run out of scenes help their CTA-mates (tail of a batch)
   int *timeout_flag;    // set to 1 if a wait on `ready` timed out (host then re-runs unstreamed)
   const int *ready;     // optional: number of scenes whose parameters have landed in d_p
                         // (host path streams p in chunks while the kernel already runs)
   unsigned long long *stats;  // [4]: cost evals, grad evals, dyn bodies, panoc iterations
+  unsigned long long *run_stats;  // [2]: evaluations and count of finished scenes (early helpers) or null
   int n_scenes;
   int use_u0, use_y0;
 };
@@ -35,6 +37,8 @@ struct EvalArgs {
 
 cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st);
 cudaError_t launch_solve_split(const DevCfg &g, const SolveArgs &A, int clusters, cudaStream_t st);
+cudaError_t launch_rank_scenes(const DevCfg &g, const double *p, int n, int *scratch, int *order,
+                               cudaStream_t st);
 cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream_t st);
 cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm);
 cudaError_t launch_probe(const DevCfg &g, const double *p, double *dyn, long long *out, int reps,
