@@ -290,6 +290,27 @@ int ttmpc_fleet_advance_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet
 int ttmpc_fleet_step_device(const ttmpc_config *cfg, const ttmpc_fleet *fleet, double *d_p,
                             int use_y0, const ttmpc_result *res, void *stream);
 
+/* ------------------------------------------------------------------------
+ * DQN side of the hybrid loop (src/main.py:174-193), device-resident.
+ *
+ * ttdqn_internal_obs_device: the `internal` observation of the ray model
+ *   (variants/rays_reward1.py:27-31): SpeedObservation, AngularVelocityObservation,
+ *   ReferencePathSampleObservation(1, 0, sample_offset), ReferencePathCornerObservation(
+ *   corner_samples) -- components/int_obsv_*.py -- with path_progress =
+ *   path.project(agent) (environment.py:115).
+ *     d_agent5   [n][5]  x y theta v w
+ *     d_path_xy  [n][max_nodes][2] reference-path polyline, d_path_n [n] node counts (>= 2)
+ *     d_internal [n][5 + 3*corner_samples] fp32 out, d_progress [n] out (may be NULL)
+ * ttdqn_rl_ref_device: the DQN "hint" trajectory: MobileRobot.step(action, ts) followed by
+ *   steps-1 x step_with_ref_speed(ts, ref_speed) on a copy of the agent
+ *   (environment/agent.py:86-145); d_rl_ref [n][steps][2] positions.
+ * ------------------------------------------------------------------------ */
+int ttdqn_internal_obs_device(int n_envs, int max_nodes, int corner_samples, double sample_offset,
+                              double max_distance, const double *d_agent5, const double *d_path_xy,
+                              const int *d_path_n, float *d_internal, double *d_progress, void *stream);
+int ttdqn_rl_ref_device(int n_envs, int steps, double ts, double ref_speed, const double *d_agent5,
+                        const int *d_action, double *d_rl_ref, void *stream);
+
 /* Cumulative device-side counters since the last reset: [0] cost-only
  * evaluations, [1] cost+gradient evaluations, [2] dynamic-obstacle bodies that
  * passed the bounding test, [3] PANOC iterations.  Synchronises the device.   */

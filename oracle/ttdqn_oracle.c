@@ -190,3 +190,110 @@ void ttdqn_oracle_observe_act(const ttdqn_scene_layout *lay, const ttdqn_qnet *q
     if (ray_out) memcpy(ray_out + (size_t)e * ns, ray, ns * sizeof(double));
   }
 }
+
+/* ------------------------------------------------------------------------------------
+ * Internal observation of the ray model and the DQN hint trajectory (rl_ref).
+ *
+ *   SpeedObservation / AngularVelocityObservation        components/int_obsv_speed.py, int_obsv_angular_velocity.py
+ *   ReferencePathSampleObservation(1, 0, offset)         components/int_obsv_reference_path_sample.py:27-39
+ *   ReferencePathCornerObservation(corner_samples)       components/int_obsv_reference_path_corner.py:21-45
+ *   env.path_progress = path.project(agent.point)        environment.py:115
+ *   MobileRobot.step / step_with_ref_speed               environment/agent.py:86-145
+ *   rl_ref loop                                           src/main.py:184-193
+ *
+ * PINNED (tests/golden/dqn_loop.npz, tools/gen_golden_dqn_loop.py): the reference's own
+ * MobileRobot and observation components run on a stand-in `shapely` module, so everything
+ * except LineString.project / interpolate is the reference's code.  project / interpolate are
+ * GEOS' length-indexed-line operations restated here (parity unpinned for those two: first
+ * closest segment wins, clamped segment fraction, linear interpolation inside a segment).
+ * ------------------------------------------------------------------------------------ */
+double ttdqn_oracle_project(const double *xy, int n, double px, double py) {
+  double best = INFINITY, best_s = 0.0, cum = 0.0;
+  for (int i = 0; i + 1 < n; i++) {
+    const double ax = xy[2 * i], ay = xy[2 * i + 1], dx = xy[2 * i + 2] - ax, dy = xy[2 * i + 3] - ay;
+    const double len2 = dx * dx + dy * dy, len = sqrt(len2);
+    double t = 0.0;
+    if (len2 > 0.0) {
+      t = ((px - ax) * dx + (py - ay) * dy) / len2;
+      t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    }
+    const double qx = ax + t * dx - px, qy = ay + t * dy - py;
+    const double d = sqrt(qx * qx + qy * qy);
+    if (d < best) { best = d; best_s = cum + t * len; }
+    cum += len;
+  }
+  return best_s;
+}
+void ttdqn_oracle_interpolate(const double *xy, int n, double s, double *x, double *y) {
+  if (s <= 0.0 || n < 2) { *x = xy[0]; *y = xy[1]; return; }
+  double cum = 0.0;
+  for (int i = 0; i + 1 < n; i++) {
+    const double ax = xy[2 * i], ay = xy[2 * i + 1], dx = xy[2 * i + 2] - ax, dy = xy[2 * i + 3] - ay;
+    const double len = sqrt(dx * dx + dy * dy);
+    if (s <= cum + len && len > 0.0) {
+      const double t = (s - cum) / len;
+      *x = ax + t * dx; *y = ay + t * dy;
+      return;
+    }
+    cum += len;
+  }
+  *x = xy[2 * (n - 1)]; *y = xy[2 * (n - 1) + 1];
+}
+static void rel_obs(double px, double py, const double *agent, double max_distance, float *o) {
+  const double dx = px - agent[0], dy = py - agent[1];
+  const double rel = atan2(dy, dx) - agent[2];
+  o[0] = (float)cos(rel);
+  o[1] = (float)sin(rel);
+  o[2] = (float)(2.0 / (1.0 + exp(-2.0 * sqrt(dx * dx + dy * dy) / max_distance)) - 1.0);
+}
+/* agent5 = x y theta v w; obs [2 + 3 + 3*corner_samples] fp32 */
+void ttdqn_oracle_internal_obs(int corner_samples, double offset, double max_distance, const double *agent5,
+                               const double *path_xy, int n_nodes, float *obs, double *progress) {
+  obs[0] = (float)(2.0 * (agent5[3] - (-0.5)) / (1.5 - (-0.5)) - 1.0);
+  /* the reference normalises the angular VELOCITY with the angular ACCELERATION bounds */
+  obs[1] = (float)(2.0 * (agent5[4] - (-3.0)) / (3.0 - (-3.0)) - 1.0);
+  const double s = ttdqn_oracle_project(path_xy, n_nodes, agent5[0], agent5[1]);
+  if (progress) *progress = s;
+  double px, py;
+  ttdqn_oracle_interpolate(path_xy, n_nodes, s + 0 * 0.0 + offset, &px, &py);
+  rel_obs(px, py, agent5, max_distance, obs + 2);
+  double length = 0.0;
+  int i = 0;
+  while (length < s) {
+    const double dx = path_xy[2 * (i + 1)] - path_xy[2 * i], dy = path_xy[2 * (i + 1) + 1] - path_xy[2 * i + 1];
+    length += sqrt(dx * dx + dy * dy);
+    i++;
+  }
+  for (int j = 0; j < corner_samples; j++) {
+    if (i > n_nodes - 1) i = n_nodes - 1;
+    rel_obs(path_xy[2 * i], path_xy[2 * i + 1], agent5, max_distance, obs + 5 + 3 * j);
+    i++;
+  }
+}
+/* rl_ref [steps][2]; use_libm = 0: the kernels' tt_sincos (bit-exact with the GPU) */
+void ttdqn_oracle_rl_ref(int steps, double ts, double ref_speed, const double *agent5, int action,
+                         double *rl_ref, int use_libm) {
+  double x = agent5[0], y = agent5[1], th = agent5[2], v = agent5[3], w = agent5[4], s, c;
+  for (int j = 0; j < steps; j++) {
+    double sp;
+    if (j == 0) {  /* MobileRobot.step(action_index, ts) */
+      if (action / 3 == 0) v += ts * 1.0;
+      if (action / 3 == 2) v += ts * -1.0;
+      if (action % 3 == 0) w += ts * 3.0;
+      if (action % 3 == 2) w += ts * -3.0;
+      if (v > 1.5) v = 1.5;
+      if (v < -0.5) v = -0.5;
+      if (w > 0.5) w = 0.5;
+      if (w < -0.5) w = -0.5;
+      th += ts * w;
+      sp = v;
+    } else {       /* step_with_ref_speed(ts, ref_speed) */
+      w *= 0.95;
+      th += ts * w;
+      sp = ref_speed <= 0.0 ? 1.5 : ref_speed;
+    }
+    if (use_libm) { s = sin(th); c = cos(th); } else ttmpc_oracle_sincos(th, &s, &c);
+    x += (ts * sp) * c; y += (ts * sp) * s;
+    rl_ref[2 * j] = x; rl_ref[2 * j + 1] = y;
+  }
+}

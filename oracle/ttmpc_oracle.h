@@ -90,6 +90,15 @@ void ttdqn_oracle_observe_act(const ttdqn_scene_layout *lay, const ttdqn_qnet *q
                               float *old_ext, float *ext, float *q, int *action,
                               double *seg_dist, double *ray_dist);
 
+/* Internal observation of the ray model and the DQN hint trajectory (see ttdqn_oracle.c). */
+double ttdqn_oracle_project(const double *xy, int n, double px, double py);
+void ttdqn_oracle_interpolate(const double *xy, int n, double s, double *x, double *y);
+void ttdqn_oracle_internal_obs(int corner_samples, double offset, double max_distance,
+                               const double *agent5, const double *path_xy, int n_nodes,
+                               float *obs, double *progress);
+void ttdqn_oracle_rl_ref(int steps, double ts, double ref_speed, const double *agent5, int action,
+                         double *rl_ref, int use_libm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,10 @@ def load():
         lib.ttmpc_oracle_eval_warp.argtypes = [CFG, VP, VP, D, VP, VP, VP, VP, VP]
         lib.ttmpc_oracle_sincos.argtypes = [D, C.POINTER(D), C.POINTER(D)]
         lib.ttdqn_oracle_observe_act.argtypes = [C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet), I] + [VP] * 12
+        lib.ttdqn_oracle_project.argtypes = [VP, I, D, D]
+        lib.ttdqn_oracle_project.restype = D
+        lib.ttdqn_oracle_internal_obs.argtypes = [I, D, D, VP, VP, I, VP, VP]
+        lib.ttdqn_oracle_rl_ref.argtypes = [I, D, D, VP, I, VP, I]
         lib.ttfleet_oracle_pack.argtypes = [CFG, C.POINTER(TtmpcFleet), VP, I]
         lib.ttfleet_oracle_advance.argtypes = [CFG, C.POINTER(TtmpcFleet), VP, VP, I]
         _lib = lib
@@ -203,3 +207,19 @@ def fleet_advance(fh: FleetHost, u, exit_status, use_libm: bool):
     es = None if exit_status is None else np.ascontiguousarray(exit_status, dtype=np.int32)
     f = fh.struct()
     lib.ttfleet_oracle_advance(C.byref(fh.cfg), C.byref(f), _p(u), _p(es), 1 if use_libm else 0)
+
+
+def internal_obs(agent5, path, corner_samples=3, offset=0.0, max_distance=10.0):
+    lib = load()
+    a = np.ascontiguousarray(agent5, np.float64); xy = np.ascontiguousarray(path, np.float64).reshape(-1, 2)
+    obs = np.zeros(5 + 3 * corner_samples, np.float32); prog = np.zeros(1)
+    lib.ttdqn_oracle_internal_obs(corner_samples, offset, max_distance, _p(a), _p(xy), len(xy), _p(obs), _p(prog))
+    return obs, float(prog[0])
+
+
+def rl_ref(agent5, action, steps=20, ts=0.2, ref_speed=1.0, use_libm=True):
+    lib = load()
+    a = np.ascontiguousarray(agent5, np.float64)
+    out = np.zeros((steps, 2))
+    lib.ttdqn_oracle_rl_ref(steps, ts, ref_speed, _p(a), int(action), _p(out), 1 if use_libm else 0)
+    return out

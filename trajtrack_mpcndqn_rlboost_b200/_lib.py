@@ -101,6 +101,8 @@ SYMBOLS = {
     "ttdqn_default_layout": (None, [_LAY]),
     "ttdqn_observe_act_device": (_I, [_LAY, _QN, _I] + [_VP] * 12 + [_VP]),
     "ttdqn_observe_act_host": (_I, [_LAY, _QN, _I] + [_VP] * 12),
+    "ttdqn_internal_obs_device": (_I, [_I, _I, _I, _D, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "ttdqn_rl_ref_device": (_I, [_I, _I, _D, _D, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None

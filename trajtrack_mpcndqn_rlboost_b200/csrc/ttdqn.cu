@@ -24,6 +24,7 @@
 #include <string>
 
 #include "../../include/ttmpc.h"
+#include "ttmpc_device.cuh"
 
 namespace ttdqn {
 
@@ -255,6 +256,109 @@ __global__ void __launch_bounds__(128) observe_act_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ internal observation, rl_ref
+// One thread per environment: a few dozen flops each, the work is the polyline walk.
+__device__ __forceinline__ void rel_obs(double px, double py, const double *agent, double max_distance, float *o) {
+  const double dx = px - agent[0], dy = py - agent[1];
+  const double rel = atan2(dy, dx) - agent[2];
+  o[0] = (float)cos(rel);
+  o[1] = (float)sin(rel);
+  o[2] = (float)(2.0 / (1.0 + exp(-2.0 * sqrt(dx * dx + dy * dy) / max_distance)) - 1.0);
+}
+__global__ void __launch_bounds__(128) internal_obs_kernel(int n, int max_nodes, int corner_samples, double offset,
+                                                           double max_distance, const double *__restrict__ agent5,
+                                                           const double *__restrict__ path_xy,
+                                                           const int *__restrict__ path_n, float *__restrict__ obs_all,
+                                                           double *__restrict__ progress) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double *a = agent5 + 5 * e, *xy = path_xy + (size_t)e * max_nodes * 2;
+  const int nn = path_n[e];
+  float *obs = obs_all + (size_t)e * (5 + 3 * corner_samples);
+  obs[0] = (float)(2.0 * (a[3] - (-0.5)) / (1.5 - (-0.5)) - 1.0);
+  obs[1] = (float)(2.0 * (a[4] - (-3.0)) / (3.0 - (-3.0)) - 1.0);  // reference quirk: acceleration bounds
+  // path.project(agent): arc length of the closest point, first closest segment wins
+  double best = INFINITY, s = 0.0, cum = 0.0;
+  for (int i = 0; i + 1 < nn; i++) {
+    const double ax = xy[2 * i], ay = xy[2 * i + 1], dx = xy[2 * i + 2] - ax, dy = xy[2 * i + 3] - ay;
+    const double len2 = dx * dx + dy * dy, len = sqrt(len2);
+    double t = 0.0;
+    if (len2 > 0.0) {
+      t = ((a[0] - ax) * dx + (a[1] - ay) * dy) / len2;
+      t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    }
+    const double qx = ax + t * dx - a[0], qy = ay + t * dy - a[1];
+    const double d = sqrt(qx * qx + qy * qy);
+    if (d < best) { best = d; s = cum + t * len; }
+    cum += len;
+  }
+  if (progress) progress[e] = s;
+  // path.interpolate(path_progress + offset)
+  {
+    const double sq = s + offset;
+    double px = xy[2 * (nn - 1)], py = xy[2 * (nn - 1) + 1];
+    if (sq <= 0.0 || nn < 2) { px = xy[0]; py = xy[1]; }
+    else {
+      double c2 = 0.0;
+      for (int i = 0; i + 1 < nn; i++) {
+        const double ax = xy[2 * i], ay = xy[2 * i + 1], dx = xy[2 * i + 2] - ax, dy = xy[2 * i + 3] - ay;
+        const double len = sqrt(dx * dx + dy * dy);
+        if (sq <= c2 + len && len > 0.0) {
+          const double t = (sq - c2) / len;
+          px = ax + t * dx; py = ay + t * dy;
+          break;
+        }
+        c2 += len;
+      }
+    }
+    rel_obs(px, py, a, max_distance, obs + 2);
+  }
+  // upcoming corners (int_obsv_reference_path_corner.py:27-43)
+  double length = 0.0;
+  int i = 0;
+  while (length < s && i + 1 < nn) {
+    const double dx = xy[2 * (i + 1)] - xy[2 * i], dy = xy[2 * (i + 1) + 1] - xy[2 * i + 1];
+    length += sqrt(dx * dx + dy * dy);
+    i++;
+  }
+  for (int j = 0; j < corner_samples; j++) {
+    if (i > nn - 1) i = nn - 1;
+    rel_obs(xy[2 * i], xy[2 * i + 1], a, max_distance, obs + 5 + 3 * j);
+    i++;
+  }
+}
+__global__ void __launch_bounds__(128) rl_ref_kernel(int n, int steps, double ts, double ref_speed,
+                                                     const double *__restrict__ agent5,
+                                                     const int *__restrict__ action_all, double *__restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double *a = agent5 + 5 * e;
+  double x = a[0], y = a[1], th = a[2], v = a[3], w = a[4], s, c;
+  const int action = action_all[e];
+  for (int j = 0; j < steps; j++) {
+    double sp;
+    if (j == 0) {  // MobileRobot.step (agent.py:120-145)
+      if (action / 3 == 0) v += ts * 1.0;
+      if (action / 3 == 2) v += ts * -1.0;
+      if (action % 3 == 0) w += ts * 3.0;
+      if (action % 3 == 2) w += ts * -3.0;
+      if (v > 1.5) v = 1.5;
+      if (v < -0.5) v = -0.5;
+      if (w > 0.5) w = 0.5;
+      if (w < -0.5) w = -0.5;
+      th += ts * w;
+      sp = v;
+    } else {       // step_with_ref_speed -> step_with_decay_angular_velocity (agent.py:86-101)
+      w *= 0.95;
+      th += ts * w;
+      sp = ref_speed <= 0.0 ? 1.5 : ref_speed;
+    }
+    ttmpc::tt_sincos(th, &s, &c);
+    x += (ts * sp) * c; y += (ts * sp) * s;
+    out[((size_t)e * steps + j) * 2] = x; out[((size_t)e * steps + j) * 2 + 1] = y;
+  }
+}
+
 }  // namespace ttdqn
 
 static thread_local std::string g_dqn_err;
@@ -379,5 +483,28 @@ extern "C" int ttdqn_observe_act_host(const ttdqn_scene_layout *lay, const ttdqn
   if (qn) { back(h_q, dqv, sizeof(float) * nn * qn->n_out); back(h_action, dact, sizeof(int) * nn); }
   cleanup();
   if (e != cudaSuccess) return dfail(TTMPC_ERR_CUDA, cudaGetErrorString(e));
+  return TTMPC_OK;
+}
+
+extern "C" int ttdqn_internal_obs_device(int n, int max_nodes, int corner_samples, double sample_offset,
+                                         double max_distance, const double *d_agent5, const double *d_path_xy,
+                                         const int *d_path_n, float *d_internal, double *d_progress, void *stream) {
+  if (n < 0 || max_nodes < 2 || corner_samples < 0 || !(max_distance > 0.0))
+    return dfail(TTMPC_ERR_BAD_ARG, "internal_obs: n >= 0, max_nodes >= 2, corner_samples >= 0, max_distance > 0");
+  if (n == 0) return TTMPC_OK;
+  if (!d_agent5 || !d_path_xy || !d_path_n || !d_internal)
+    return dfail(TTMPC_ERR_BAD_ARG, "internal_obs: agent, path and output pointers are required");
+  ttdqn::internal_obs_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      n, max_nodes, corner_samples, sample_offset, max_distance, d_agent5, d_path_xy, d_path_n, d_internal, d_progress);
+  DQN_TRY(cudaGetLastError());
+  return TTMPC_OK;
+}
+extern "C" int ttdqn_rl_ref_device(int n, int steps, double ts, double ref_speed, const double *d_agent5,
+                                   const int *d_action, double *d_rl_ref, void *stream) {
+  if (n < 0 || steps < 1 || !(ts > 0.0)) return dfail(TTMPC_ERR_BAD_ARG, "rl_ref: n >= 0, steps >= 1, ts > 0");
+  if (n == 0) return TTMPC_OK;
+  if (!d_agent5 || !d_action || !d_rl_ref) return dfail(TTMPC_ERR_BAD_ARG, "rl_ref: null pointer");
+  ttdqn::rl_ref_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, steps, ts, ref_speed, d_agent5, d_action, d_rl_ref);
+  DQN_TRY(cudaGetLastError());
   return TTMPC_OK;
 }

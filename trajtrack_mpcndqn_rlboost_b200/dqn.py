@@ -134,3 +134,50 @@ class DqnCompanion:
         if rc != 0:
             raise _lib.TtmpcError(f"ttdqn_observe_act_device failed (code {rc})")
         return out
+
+
+def pack_paths(paths, max_nodes: int = None):
+    """Reference-path polylines -> (xy [n][max_nodes][2] float64, count [n] int32)."""
+    n = len(paths)
+    m = max_nodes or max(len(p) for p in paths)
+    xy = np.zeros((n, m, 2), np.float64)
+    cnt = np.zeros(n, np.int32)
+    for i, p in enumerate(paths):
+        a = np.asarray(p, np.float64).reshape(-1, 2)
+        xy[i, :len(a)] = a
+        cnt[i] = len(a)
+    return xy, cnt
+
+
+def internal_obs_device(agent5, path_xy, path_n, corner_samples: int = 3, sample_offset: float = 0.0,
+                        max_distance: float = 10.0, out=None, progress=None, stream=None):
+    """``internal`` observation of the ray model (rays_reward1.py:27-31) for n environments.
+    agent5 [n][5] (x y theta v w), path_xy [n][m][2], path_n [n]: CUDA torch tensors.
+    Returns (internal [n][5 + 3*corner_samples] float32, path_progress [n] float64)."""
+    import torch
+    n = agent5.shape[0]
+    if out is None:
+        out = torch.empty(n, 5 + 3 * corner_samples, dtype=torch.float32, device=agent5.device)
+    if progress is None:
+        progress = torch.empty(n, dtype=torch.float64, device=agent5.device)
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    rc = _lib.load().ttdqn_internal_obs_device(n, path_xy.shape[1], corner_samples, float(sample_offset),
+                                               float(max_distance), agent5.data_ptr(), path_xy.data_ptr(),
+                                               path_n.data_ptr(), out.data_ptr(), progress.data_ptr(), C.c_void_p(st))
+    if rc != 0:
+        raise _lib.TtmpcError(f"ttdqn_internal_obs_device failed (code {rc})")
+    return out, progress
+
+
+def rl_ref_device(agent5, action, steps: int = 20, ts: float = 0.2, ref_speed: float = 1.0, out=None, stream=None):
+    """The DQN hint trajectory of main.py:184-193: positions [n][steps][2] (float64)."""
+    import torch
+    n = agent5.shape[0]
+    if out is None:
+        out = torch.empty(n, steps, 2, dtype=torch.float64, device=agent5.device)
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    rc = _lib.load().ttdqn_rl_ref_device(n, steps, float(ts), float(ref_speed), agent5.data_ptr(), action.data_ptr(),
+                                         out.data_ptr(), C.c_void_p(st))
+    if rc != 0:
+        raise _lib.TtmpcError(f"ttdqn_rl_ref_device failed (code {rc})")
+    return out
