@@ -276,6 +276,11 @@ typedef struct ttmpc_fleet {
   double tuning[10];      /* q block (set_work_mode, trajectory_generator.py:117-131) */
   double base_speed, low_speed;
   double stc_weight, dyn_weight;
+  /* hybrid mode (main.py:194-201): where use_hint[e] != 0 the N reference positions are the
+   * DQN hint hint[e] (rl_ref) and the headings stay those of the original local reference
+   * (InterfaceMpc.get_local_ref_traj(rl_ref) + ref_traj_filter(decay = 1)).  NULL = never. */
+  const double *hint;     /* [n][N][2] */
+  const int *use_hint;    /* [n]       */
 } ttmpc_fleet;
 
 /* d_p [n][np] is written for every robot (robots that are not RUNNING keep packing from

@@ -62,12 +62,17 @@ void ttfleet_oracle_pack(const ttmpc_config *g, const ttmpc_fleet *f, double *p_
     }
     int o = 0;
     for (int i = 0; i < 3; i++) p[o++] = st[i];
-    { int r = idx + N - 1; if (r > L - 1) r = L - 1; for (int i = 0; i < 3; i++) p[o++] = ref[3 * r + i]; }
+    const int hinted = f->hint && f->use_hint && f->use_hint[e];
+    const double *hint = hinted ? f->hint + (size_t)e * N * 2 : 0;
+    {
+      int r = idx + N - 1; if (r > L - 1) r = L - 1;
+      for (int i = 0; i < 3; i++) p[o++] = (hinted && i < 2) ? hint[2 * (N - 1) + i] : ref[3 * r + i];
+    }
     p[o++] = lu[0]; p[o++] = lu[1];
     for (int i = 0; i < 10; i++) p[o++] = f->tuning[i];
     for (int k = 0; k < N; k++) {
       int r = idx + k; if (r > L - 1) r = L - 1;
-      for (int i = 0; i < 3; i++) p[o++] = ref[3 * r + i];
+      for (int i = 0; i < 3; i++) p[o++] = (hinted && i < 2) ? hint[2 * k + i] : ref[3 * r + i];
     }
     {
       const double dist = hyp(st[0] - goal[0], st[1] - goal[1], use_libm);

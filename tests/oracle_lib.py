@@ -171,6 +171,8 @@ class FleetHost:
         self.dyn_cur = None if dyn_cur is None else f64(dyn_cur).copy()
         self.dyn_last = None if dyn_cur is None else f64(dyn_cur).copy()
         self.dyn_disp = None if dyn_disp is None else f64(dyn_disp)
+        self.hint = None
+        self.use_hint = None
 
     def struct(self):
         f = TtmpcFleet()
@@ -187,6 +189,10 @@ class FleetHost:
             f.tuning[i] = float(v)
         f.base_speed, f.low_speed = self.base_speed, self.low_speed
         f.stc_weight, f.dyn_weight = self.stc_weight, self.dyn_weight
+        if self.hint is not None:
+            self.hint = np.ascontiguousarray(self.hint, dtype=np.float64)
+            self.use_hint = np.ascontiguousarray(self.use_hint, dtype=np.int32)
+            f.hint, f.use_hint = _p(self.hint), _p(self.use_hint)
         return f
 
 

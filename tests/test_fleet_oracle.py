@@ -81,3 +81,31 @@ def test_solver_failure_freezes_the_robot():
     assert int(fh.status[0]) == 2 and np.array_equal(fh.state, before)
     O.fleet_advance(fh, G[k + "u"][None], np.zeros(1, np.int32), True)     # stays frozen
     assert np.array_equal(fh.state, before)
+
+
+def test_hint_matches_interface_mpc_semantics():
+    """Hybrid mode: InterfaceMpc.get_local_ref_traj(rl_ref) appends the original headings to the
+    hint positions (interface_mpc.py:76-78) and ref_traj_filter(decay=1) keeps the hint
+    (main.py:35-42); run_step then packs that trajectory (finish_state = its last row)."""
+    mc = t.Configurator()
+    cfg = mc.to_ttmpc()
+    off = t.param_offsets(cfg)
+    N = cfg.N_hor
+    fh, k = _host(cfg, mc, 1, 2)
+    p0 = O.fleet_pack(fh, True)[0].copy()
+    fh.idx_ref[:] = int(G[k + "idx"])
+    rng = np.random.default_rng(0)
+    hint = rng.normal(0, 3, (1, N, 2))
+    fh.hint, fh.use_hint = hint, np.ones(1, np.int32)
+    p1 = O.fleet_pack(fh, True)[0]
+    original = p0[off["r"]:off["r"] + 3 * N].reshape(N, 3)
+    local = np.concatenate((hint[0], original[:, [2]]), axis=1)          # interface_mpc.py:77
+    filtered = original.copy()                                           # main.py:35-42 with decay = 1
+    decay = 1
+    for i in range(N):
+        filtered[i, :] = (1 - decay) * filtered[i, :] + decay * local[i, :]
+        decay *= decay
+    expect = p0.copy()
+    expect[off["r"]:off["r"] + 3 * N] = filtered.reshape(-1)
+    expect[3:6] = filtered[-1]
+    assert np.array_equal(p1, expect)

@@ -81,3 +81,29 @@ def test_fleet_matches_single_robot_mirror():
     fp.step(); fp.torch.cuda.synchronize()
     np.testing.assert_allclose(fp.state.cpu().numpy()[0], one.state, rtol=0, atol=1e-12)
     np.testing.assert_allclose(fp.last_u.cpu().numpy()[0], action, rtol=0, atol=1e-12)
+
+
+def test_pack_with_dqn_hint_bit_exact():
+    """Hybrid mode: hinted robots take rl_ref positions, headings from the original window --
+    what InterfaceMpc.get_local_ref_traj(rl_ref) + ref_traj_filter(decay=1) produce."""
+    import torch
+    fp, fh = _make(40, seed=6)
+    agent5 = torch.cat([fp.state, torch.rand(40, 2, dtype=torch.float64, device="cuda") - 0.3], dim=1).contiguous()
+    act = torch.randint(0, 9, (40,), dtype=torch.int32, device="cuda")
+    rl = t.dqn.rl_ref_device(agent5, act)
+    use = (torch.arange(40, device="cuda") % 3 != 0).to(torch.int32)
+    fp.set_hint(rl, use)
+    fh.hint, fh.use_hint = rl.cpu().numpy(), use.cpu().numpy()
+    fp.pack(); torch.cuda.synchronize()
+    p_ref = O.fleet_pack(fh, use_libm=False)
+    p_dev = fp.p.cpu().numpy()
+    assert np.array_equal(p_dev, p_ref)
+    # against the single-robot mirror for one hinted robot
+    off = t.param_offsets(fp.cfg); N = fp.N
+    e = 1
+    refs = p_dev[e, off["r"]:off["r"] + 3 * N].reshape(N, 3)
+    assert np.array_equal(refs[:, :2], rl.cpu().numpy()[e])
+    fh.use_hint[:] = 0
+    p_plain = O.fleet_pack(fh, use_libm=False)
+    assert np.array_equal(refs[:, 2], p_plain[e, off["r"]:off["r"] + 3 * N].reshape(N, 3)[:, 2])
+    assert np.array_equal(p_dev[e, 3:5], rl.cpu().numpy()[e, -1]) and p_dev[e, 5] == p_plain[e, 5]

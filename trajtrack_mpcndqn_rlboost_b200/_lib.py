@@ -70,6 +70,7 @@ class TtmpcFleet(C.Structure):
         ("dyn_size", C.c_double), ("tuning", C.c_double * 10),
         ("base_speed", C.c_double), ("low_speed", C.c_double),
         ("stc_weight", C.c_double), ("dyn_weight", C.c_double),
+        ("hint", C.c_void_p), ("use_hint", C.c_void_p),
     ]
 
 

@@ -61,16 +61,21 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
   const int o_refs = 18, o_speed = o_refs + 3 * N, o_other = o_speed + N, o_stc = o_other + d.n_other,
             o_dyn = o_stc + d.n_stc, o_ws = o_dyn + d.n_dyn, o_wd = o_ws + N;
   const double *stc = f.stc + (f.stc_shared ? 0 : (size_t)e * d.n_stc);
+  const bool hinted = f.hint && f.use_hint && f.use_hint[e];  // hybrid mode: DQN hint positions
+  const double *hint = f.hint + (size_t)e * N * 2;
   for (int o = threadIdx.x; o < d.np; o += blockDim.x) {
     double v;
     if (o < 3) v = st[o];
-    else if (o < 6) { int r = idx + N - 1; if (r > L - 1) r = L - 1; v = ref[3 * r + (o - 3)]; }
+    else if (o < 6) {
+      int r = idx + N - 1; if (r > L - 1) r = L - 1;
+      v = (hinted && o < 5) ? hint[2 * (N - 1) + (o - 3)] : ref[3 * r + (o - 3)];
+    }
     else if (o < 8) v = lu[o - 6];
     else if (o < o_refs) v = f.tuning[o - 8];
     else if (o < o_speed) {
       const int k = (o - o_refs) / 3, c = (o - o_refs) - 3 * k;
       int r = idx + k; if (r > L - 1) r = L - 1;
-      v = ref[3 * r + c];
+      v = (hinted && c < 2) ? hint[2 * k + c] : ref[3 * r + c];
     }
     else if (o < o_other) v = s_speed;
     else if (o < o_stc) v = f.other ? f.other[(size_t)e * d.n_other + (o - o_other)] : 0.0;

@@ -87,6 +87,8 @@ class FleetPlanner:
         self.exit_status = torch.zeros(n, **i32)
         self.inner = torch.zeros(n, **i32)
         self.pred_states = torch.zeros(n, self.N, 3, **f64)
+        self.hint = None       # [n][N][2] DQN hint positions (rl_ref) and the per-robot switch
+        self.use_hint = None
         self.steps = 0
 
     # ------------------------------------------------------------------ obstacles
@@ -116,6 +118,11 @@ class FleetPlanner:
         self.dyn_last = t.tensor(pos, device=dev)
         self.dyn_disp = t.tensor(np.asarray(displacement_per_step, dtype=np.float64).reshape(self.n, -1, 2), device=dev)
 
+    def set_hint(self, rl_ref, use_hint):
+        """Hybrid mode (main.py:194-201): rl_ref [n][N][2] float64 CUDA tensor (dqn.rl_ref_device),
+        use_hint [n] int32 -- where non-zero the hint replaces the reference positions."""
+        self.hint, self.use_hint = rl_ref, use_hint
+
     # ------------------------------------------------------------------ the step
     def _fleet_struct(self) -> _lib.TtmpcFleet:
         f = _lib.TtmpcFleet()
@@ -134,6 +141,8 @@ class FleetPlanner:
             f.tuning[i] = float(v)
         f.base_speed, f.low_speed = float(self.base_speed), float(self.config.low_speed)
         f.stc_weight, f.dyn_weight = self.stc_weight, self.dyn_weight
+        if self.hint is not None and self.use_hint is not None:
+            f.hint, f.use_hint = self.hint.data_ptr(), self.use_hint.data_ptr()
         return f
 
     def _result_struct(self) -> _lib.TtmpcResult:
