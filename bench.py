@@ -236,8 +236,8 @@ def main():
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch on this
-                # workload, ncu --set full capture profiles/r1_c_solve_kernel_final.txt
-                "traffic": 135.4e6 if args.workload == "static4096" else None,
+                # workload, ncu --set full capture profiles/r1_e_solve_kernel_final.txt
+                "traffic": 145.7e6 if args.workload == "static4096" else None,
                 "peak_source": "measured live: DFMA probe kernel (ttmpc_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "hbm_GBps_algorithmic": (p_host.nbytes + d2h) / (local_ms * 1e-3) / 1e9,
@@ -272,7 +272,9 @@ def main():
                        "launch": info},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step * 1e3},
-            "gpu_launches": args.steps,
+            # per step: solve_kernel, plus rank_scenes_kernel + order_scenes_kernel when the batch
+            # is larger than the resident warps (dispatch order)
+            "gpu_launches": args.steps * (3 if n > info["grid"] * info["block"] // 32 else 1),
             "clocks": summarize_clocks(samples),
             "roofline": roofline,
             "cpu_baseline": cpu,
