@@ -25,6 +25,19 @@
 
 #include "../../include/ttmpc.h"
 
+// Unroll policy of the hot loops.  The kernel is bound by instruction-cache refills (DESIGN.md
+// section 6), so every unroll factor is a trade between dependent-issue latency and code bytes;
+// -DTTMPC_SMALL_CODE builds the variant with every hot loop rolled.
+#ifdef TTMPC_SMALL_CODE
+#define TT_UNROLL_SCAN _Pragma("unroll 1")
+#define TT_UNROLL_2 _Pragma("unroll 1")
+#define TT_UNROLL_4 _Pragma("unroll 1")
+#else
+#define TT_UNROLL_SCAN _Pragma("unroll")
+#define TT_UNROLL_2 _Pragma("unroll 2")
+#define TT_UNROLL_4 _Pragma("unroll 4")
+#endif
+
 namespace ttmpc {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -74,13 +87,13 @@ __host__ __device__ __forceinline__ void tt_sincos(double x, double *s, double *
 
 // ---------------------------------------------------------------- warp utils
 static __device__ __noinline__ double wsum(double v) {
-#pragma unroll
+TT_UNROLL_SCAN
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
 struct D3 { double a, b, c; };
 static __device__ __noinline__ D3 wsum3v(double a, double b, double c) {
-#pragma unroll
+TT_UNROLL_SCAN
   for (int o = 16; o > 0; o >>= 1) {
     double ta = __shfl_xor_sync(FULL, a, o);
     double tb = __shfl_xor_sync(FULL, b, o);
@@ -96,7 +109,7 @@ __device__ __forceinline__ void wsum3(double &a, double &b, double &c) {
 }
 // inclusive prefix sum over lanes (Kogge-Stone)
 __device__ __forceinline__ double wscan(double v, int lane) {
-#pragma unroll
+TT_UNROLL_SCAN
   for (int o = 1; o < 32; o <<= 1) {
     double t = __shfl_up_sync(FULL, v, o);
     if (lane >= o) v += t;
@@ -105,7 +118,7 @@ __device__ __forceinline__ double wscan(double v, int lane) {
 }
 // inclusive suffix sum over lanes
 __device__ __forceinline__ double wsuffix(double v, int lane) {
-#pragma unroll
+TT_UNROLL_SCAN
   for (int o = 1; o < 32; o <<= 1) {
     double t = __shfl_down_sync(FULL, v, o);
     if (lane + o < 32) v += t;
@@ -427,7 +440,7 @@ struct EvalOut {
 
 struct D4 { double a, b, c, d; };
 static __device__ __noinline__ D4 wsum4v(double a, double b, double c, double d) {
-#pragma unroll
+TT_UNROLL_SCAN
   for (int o = 16; o > 0; o >>= 1) {
     const double ta = __shfl_xor_sync(FULL, a, o), tb = __shfl_xor_sync(FULL, b, o);
     const double tc = __shfl_xor_sync(FULL, c, o), td = __shfl_xor_sync(FULL, d, o);
@@ -489,7 +502,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   double X, Y;
   {  // two prefix scans, interleaved
     double a = dx, b = dy;
-#pragma unroll
+TT_UNROLL_SCAN
     for (int o = 1; o < 32; o <<= 1) {
       const double ta = __shfl_up_sync(FULL, a, o), tb = __shfl_up_sync(FULL, b, o);
       if (lane >= o) { a += ta; b += tb; }
@@ -524,7 +537,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     const int trips = (nh >= N) ? (N + 1) / 2 : max((N + 1) / 2, N - nh);
     double dmin = INFINITY; int jmin = lo;
     const double2 *segv = reinterpret_cast<const double2 *>(sm.seg);
-#pragma unroll 2
+TT_UNROLL_2
     for (int t = 0; t < trips; t++) {
       const int j = min(lo + t, N - 1);
       const double2 s1 = segv[3 * j], sd = segv[3 * j + 1];
@@ -694,7 +707,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   //      flag, one vote, second pass over the flagged obstacles in the same order.
   {
     unsigned in_mask = 0;  // Nstcobs <= 32
-#pragma unroll 4
+TT_UNROLL_4
     for (int i = 0; i < Nstc; i++) {
       const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
       double inside = 1.0;
@@ -817,7 +830,7 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
     const double hvt = hv * ts;
     const double dxdw = -(hvt * fma(2.0, sb, sc)), dydw = hvt * fma(2.0, cb, cc);
     double lx = gx, ly = gy;
-#pragma unroll
+TT_UNROLL_SCAN
     for (int o = 1; o < 32; o <<= 1) {
       const double ta = __shfl_down_sync(FULL, lx, o), tb = __shfl_down_sync(FULL, ly, o);
       if (lane + o < 32) { lx += ta; ly += tb; }

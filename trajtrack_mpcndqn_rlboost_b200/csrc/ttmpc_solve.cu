@@ -174,7 +174,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   __syncwarp();
   double wv = yq;
   if (lane < m) {
-#pragma unroll 4
+TT_UNROLL_4
     for (int c = 0; c < m; c++) wv = fma(-sm.alpha[c], sm.gyy[pme * M1 + lb_slot<DM>(g, U, c)], wv);
   }
   wv = U.lb_gamma * wv;
@@ -192,13 +192,13 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   // d = gamma q - sum_c (gamma a_c) y_c + sum_c cc_c s_c   (newest-to-oldest, then oldest-to-newest)
   double q0 = U.lb_gamma * z.d0, q1 = U.lb_gamma * z.d1;
   if (act) {
-#pragma unroll 2
+TT_UNROLL_2
     for (int c = 0; c < m; c++) {
       const double2 y = sm.lby[lb_slot<DM>(g, U, c) * NP + lane];
       const double ga = sm.alpha[c];
       q0 = fma(-ga, y.x, q0); q1 = fma(-ga, y.y, q1);
     }
-#pragma unroll 2
+TT_UNROLL_2
     for (int c = m - 1; c >= 0; c--) {
       const double2 s = sm.lbs[lb_slot<DM>(g, U, c) * NP + lane];
       const double cf = sm.alpha[M1 + c];
