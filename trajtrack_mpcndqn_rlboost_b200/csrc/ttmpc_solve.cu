@@ -558,6 +558,7 @@ __device__ bool help_long_running_mate(const DevCfg &g, const SolveArgs &A, CtaH
 template <class DM, bool SP>
 __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, int lane, const Problem &pb,
                            Lane &z, Uni &U, double tolerance, HelpCtl &hc) {
+  PROF_BEGIN(t_step)
   if (U.iteration >= 1) { z.gp0 = z.g0; z.gp1 = z.g1; }
   compute_fpr(z, U);
   if (__builtin_expect(U.norm_fpr < tolerance, 0)) {
@@ -572,13 +573,20 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   {
     double cost_half;
     if (__builtin_expect(help_available<SP>(hc), SP ? 1 : 0)) {
+      PROF_BEGIN(tp)
       help_post<SP>(hc, sm, lane, DM::N(g), z.h0, z.h1, pb.c, 0, 0.0);
+      PROF_END(tp, 4)  // helper timeline: post
       const int s_first = U.lb_first, s_head = U.lb_head, s_active = U.lb_active;
       const double s_gamma = U.lb_gamma, s_os0 = z.os0, s_os1 = z.os1, s_og0 = z.og0, s_og1 = z.og1;
+      PROF_BEGIN(tl)
       lbfgs_update<DM>(g, sm, z, U, lane);
       if (U.iteration > 0) { z.d0 = z.f0; z.d1 = z.f1; lbfgs_apply<DM>(g, sm, z, U, lane); }
+      PROF_END(tl, 5)  // speculative L-BFGS
       EvalOut r;
-      if (hc.pending && help_wait<SP>(hc, sm, lane, DM::N(g), r)) {
+      PROF_BEGIN(tw)
+      const bool got = hc.pending && help_wait<SP>(hc, sm, lane, DM::N(g), r);
+      PROF_END(tw, 6)  // waiting for the helper's psi(u_half)
+      if (got) {
         cost_half = r.psi;
         if (lane == 0) sm.ctx->n_cost++;
       } else {
@@ -709,6 +717,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
     z.u0 = p0; z.u1 = p1;
   }
   U.iteration++;
+  PROF_END(t_step, 7)  // whole step
   return true;
 }
 
@@ -895,6 +904,9 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     wstats[6] += sm.ctx->prof[2] + sm.ctx->prof[3];
     wstats[7] += clock64() - t_clk0;
     sm.ctx->eprof[9] = sm.ctx->prof[3];  // L-BFGS apply alone (slot 6 holds update + apply)
+#ifdef TTMPC_PROFILE_HELP
+    for (int i = 0; i < 4; i++) sm.ctx->eprof[i] = sm.ctx->prof[4 + i];  // helper timeline instead of eval sections
+#endif
     if (A.eprof) for (int i = 0; i < 10; i++) atomicAdd(A.eprof + i, (unsigned long long)sm.ctx->eprof[i]);
 #endif
   }
