@@ -280,7 +280,17 @@ typedef struct ttmpc_fleet {
    * DQN hint hint[e] (rl_ref) and the headings stay those of the original local reference
    * (InterfaceMpc.get_local_ref_traj(rl_ref) + ref_traj_filter(decay = 1)).  NULL = never. */
   const double *hint;     /* [n][N][2] */
-  const int *use_hint;    /* [n]       */
+  int *use_hint;          /* [n] input -- or OUTPUT when sw_state != NULL             */
+  /* HintSwitcher.switch (main_pre.py:27-52), evaluated by the pack kernel when sw_state != NULL
+   * with the robot position, the ORIGINAL local reference and the obstacle list
+   * "processed static polygons + circle_to_rect(moving obstacle)" (main.py:91-95,200):
+   * shapely Polygon.contains / distance restated (interior strictly, 0 inside).      */
+  int *sw_state;            /* [n][2] switch_on, detach_cnt (in/out) or NULL           */
+  const double *sw_poly_xy; /* [n or 1][sw_max_poly][sw_max_pv][2] static polygons      */
+  const int *sw_poly_nv;    /* [n or 1][sw_max_poly] vertex counts (0 = unused slot)    */
+  int sw_max_poly, sw_max_pv, sw_poly_shared, sw_detach_steps;
+  double sw_switch_distance, sw_detach_distance; /* HintSwitcher(10, 2, 10) in main.py:129 */
+  double sw_dyn_radius;     /* circle_to_rect radius (main.py:91: DYN_OBS_SIZE)         */
 } ttmpc_fleet;
 
 /* d_p [n][np] is written for every robot (robots that are not RUNNING keep packing from

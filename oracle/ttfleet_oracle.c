@@ -37,6 +37,64 @@ static int np_of(const ttmpc_config *g) {
          g->Nstcobs * g->nstcobs + g->Ndynobs * g->ndynobs * N + 2 * N;
 }
 
+/* shapely Polygon.contains(Point): strictly inside (even-odd rule); Polygon.distance(Point):
+ * 0 inside, else the distance to the closest edge. */
+static int poly_contains(const double *xy, int nv, double px, double py) {
+  int in = 0;
+  for (int i = 0, j = nv - 1; i < nv; j = i++) {
+    const double xi = xy[2 * i], yi = xy[2 * i + 1], xj = xy[2 * j], yj = xy[2 * j + 1];
+    if (((yi > py) != (yj > py)) && (px < (xj - xi) * (py - yi) / (yj - yi) + xi)) in = !in;
+  }
+  return in;
+}
+static double poly_distance(const double *xy, int nv, double px, double py) {
+  if (poly_contains(xy, nv, px, py)) return 0.0;
+  double best = INFINITY;
+  for (int i = 0, j = nv - 1; i < nv; j = i++) {
+    const double ax = xy[2 * j], ay = xy[2 * j + 1], dx = xy[2 * i] - ax, dy = xy[2 * i + 1] - ay;
+    const double len2 = dx * dx + dy * dy;
+    double t = 0.0;
+    if (len2 > 0.0) { t = ((px - ax) * dx + (py - ay) * dy) / len2; t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); }
+    const double qx = ax + t * dx - px, qy = ay + t * dy - py;
+    const double d = sqrt(qx * qx + qy * qy);
+    if (d < best) best = d;
+  }
+  return best;
+}
+/* HintSwitcher.switch (main_pre.py:35-52) for robot e; ref rows are the ORIGINAL local reference */
+static int hint_switch(const ttmpc_fleet *f, int e, int N, const double *ref, int L, int idx) {
+  int *st = f->sw_state + 2 * e;   /* switch_on, detach_cnt */
+  const double px = f->state[3 * e], py = f->state[3 * e + 1];
+  const int n_stc = f->sw_poly_xy ? f->sw_max_poly : 0;
+  const int n_dyn = f->dyn_cur ? f->n_dyn_live : 0;
+  const double *pxy = f->sw_poly_xy ? f->sw_poly_xy + (f->sw_poly_shared ? 0 : (size_t)e * f->sw_max_poly * f->sw_max_pv * 2) : 0;
+  const int *pnv = f->sw_poly_nv ? f->sw_poly_nv + (f->sw_poly_shared ? 0 : (size_t)e * f->sw_max_poly) : 0;
+  int cnt_flag = 0;
+  for (int k = 0; k < N; k++) {
+    int r = idx + k; if (r > L - 1) r = L - 1;
+    const double ox = ref[3 * r], oy = ref[3 * r + 1];
+    for (int o = 0; o < n_stc + n_dyn; o++) {
+      double rect[8];
+      const double *xy; int nv;
+      if (o < n_stc) { nv = pnv[o]; xy = pxy + (size_t)o * f->sw_max_pv * 2; if (nv < 3) continue; }
+      else {  /* circle_to_rect (main.py:91-95) */
+        const double *c = f->dyn_cur + ((size_t)e * f->n_dyn_live + (o - n_stc)) * 2, rr = f->sw_dyn_radius;
+        rect[0] = c[0] - rr; rect[1] = c[1] - rr; rect[2] = c[0] + rr; rect[3] = c[1] - rr;
+        rect[4] = c[0] + rr; rect[5] = c[1] + rr; rect[6] = c[0] - rr; rect[7] = c[1] + rr;
+        xy = rect; nv = 4;
+      }
+      const double dist = poly_distance(xy, nv, px, py);
+      if (poly_contains(xy, nv, ox, oy)) {
+        if (dist < f->sw_switch_distance && !st[0]) { st[0] = 1; return 1; }
+      } else if (dist > f->sw_detach_distance && st[0]) {
+        if (st[1] > f->sw_detach_steps) { st[0] = 0; st[1] = 0; }
+        else if (!cnt_flag) { st[1] += 1; cnt_flag = 1; }
+      }
+    }
+  }
+  return st[0];
+}
+
 void ttfleet_oracle_pack(const ttmpc_config *g, const ttmpc_fleet *f, double *p_all, int use_libm) {
   const int N = g->N_hor, np = np_of(g);
   for (int e = 0; e < f->n; e++) {
@@ -45,6 +103,7 @@ void ttfleet_oracle_pack(const ttmpc_config *g, const ttmpc_fleet *f, double *p_
     const double *ref = f->ref_traj + (size_t)e * f->ref_stride * 3;
     const int L = f->ref_len[e];
     int idx = f->idx_ref[e];
+    const int was_running = f->status[e] == TTMPC_FLEET_RUNNING;
     if (f->status[e] == TTMPC_FLEET_RUNNING) {
       /* get_local_ref_traj: closest point in [idx - action_steps, idx + 5 action_steps) */
       int lo = idx - 1 * f->action_steps; if (lo < 0) lo = 0;
@@ -62,6 +121,9 @@ void ttfleet_oracle_pack(const ttmpc_config *g, const ttmpc_fleet *f, double *p_
     }
     int o = 0;
     for (int i = 0; i < 3; i++) p[o++] = st[i];
+    /* main.py:200 evaluates the switch before get_action's goal test */
+    if (f->sw_state && f->hint && f->use_hint && was_running)
+      f->use_hint[e] = hint_switch(f, e, N, ref, L, idx);
     const int hinted = f->hint && f->use_hint && f->use_hint[e];
     const double *hint = hinted ? f->hint + (size_t)e * N * 2 : 0;
     {

@@ -173,6 +173,9 @@ class FleetHost:
         self.dyn_disp = None if dyn_disp is None else f64(dyn_disp)
         self.hint = None
         self.use_hint = None
+        self.sw_state = None     # HintSwitcher: set sw_state [n][2] int32, sw_poly_xy [n|1][P][V][2], sw_poly_nv [n|1][P]
+        self.sw_poly_xy = self.sw_poly_nv = None
+        self.sw_params = (10.0, 2.0, 10)
 
     def struct(self):
         f = TtmpcFleet()
@@ -193,6 +196,15 @@ class FleetHost:
             self.hint = np.ascontiguousarray(self.hint, dtype=np.float64)
             self.use_hint = np.ascontiguousarray(self.use_hint, dtype=np.int32)
             f.hint, f.use_hint = _p(self.hint), _p(self.use_hint)
+        if self.sw_state is not None:
+            self.sw_state = np.ascontiguousarray(self.sw_state, dtype=np.int32)
+            self.sw_poly_xy = np.ascontiguousarray(self.sw_poly_xy, dtype=np.float64)
+            self.sw_poly_nv = np.ascontiguousarray(self.sw_poly_nv, dtype=np.int32)
+            f.sw_state, f.sw_poly_xy, f.sw_poly_nv = _p(self.sw_state), _p(self.sw_poly_xy), _p(self.sw_poly_nv)
+            f.sw_max_poly, f.sw_max_pv = self.sw_poly_xy.shape[1], self.sw_poly_xy.shape[2]
+            f.sw_poly_shared = 1 if self.sw_poly_xy.shape[0] == 1 and self.n != 1 else (1 if self.sw_poly_xy.shape[0] == 1 else 0)
+            f.sw_switch_distance, f.sw_detach_distance, f.sw_detach_steps = self.sw_params
+            f.sw_dyn_radius = 1.6
         return f
 
 

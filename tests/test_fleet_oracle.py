@@ -109,3 +109,99 @@ def test_hint_matches_interface_mpc_semantics():
     expect[off["r"]:off["r"] + 3 * N] = filtered.reshape(-1)
     expect[3:6] = filtered[-1]
     assert np.array_equal(p1, expect)
+
+
+# ------------------------------------------------------------------ HintSwitcher
+class _Poly:
+    """Minimal stand-in for shapely's Polygon (contains: strict interior; distance: 0 inside)."""
+    def __init__(self, pts):
+        self.p = [tuple(map(float, q)) for q in pts]
+
+    def contains(self, pt):
+        x, y = pt
+        inside = False
+        n = len(self.p)
+        for i in range(n):
+            (xi, yi), (xj, yj) = self.p[i], self.p[i - 1]
+            if (yi > y) != (yj > y) and x < (xj - xi) * (y - yi) / (yj - yi) + xi:
+                inside = not inside
+        return inside
+
+    def distance(self, pt):
+        if self.contains(pt):
+            return 0.0
+        x, y = pt
+        best = float("inf")
+        n = len(self.p)
+        for i in range(n):
+            (ax, ay), (bx, by) = self.p[i - 1], self.p[i]
+            dx, dy = bx - ax, by - ay
+            l2 = dx * dx + dy * dy
+            tt = 0.0 if l2 == 0 else min(1.0, max(0.0, ((x - ax) * dx + (y - ay) * dy) / l2))
+            best = min(best, ((ax + tt * dx - x) ** 2 + (ay + tt * dy - y) ** 2) ** 0.5)
+        return best
+
+
+class _HintSwitcher:
+    """main_pre.py:27-52, transcribed statement for statement (Polygon -> _Poly)."""
+    def __init__(self, max_switch_distance, min_detach_distance, min_detach_steps=5):
+        self.switch_distance = max_switch_distance
+        self.detach_distance = min_detach_distance
+        self.detach_steps = min_detach_steps
+        self.detach_cnt = 0
+        self.switch_on = False
+
+    def switch(self, current_position, original_traj, new_traj, obstacle_list):
+        cnt_flag = False
+        for old_pos, new_pos in zip(original_traj, new_traj):
+            for obstacle in obstacle_list:
+                shapely_obstacle = _Poly(obstacle)
+                dist = shapely_obstacle.distance(tuple(current_position))
+                if shapely_obstacle.contains(tuple(old_pos[:2])):
+                    if (dist < self.switch_distance) & (self.switch_on == False):  # noqa: E712
+                        self.switch_on = True
+                        return self.switch_on
+                elif (dist > self.detach_distance) & (self.switch_on == True):  # noqa: E712
+                    if self.detach_cnt > self.detach_steps:
+                        self.switch_on = False
+                        self.detach_cnt = 0
+                    elif cnt_flag == False:  # noqa: E712
+                        self.detach_cnt += 1
+                        cnt_flag = True
+        return self.switch_on
+
+
+def test_hint_switch_state_machine():
+    """The pack oracle's switch decision over a drive past an obstacle that sits on the reference:
+    on when close, off again detach_steps + 2 steps after leaving it (main.py:129: HintSwitcher(10, 2, 10))."""
+    mc = t.Configurator()
+    cfg = mc.to_ttmpc()
+    N = cfg.N_hor
+    tuning, base = work_mode(mc, "work")
+    ref = np.stack([np.arange(400) * 0.24, np.zeros(400), np.zeros(400)], axis=1)       # straight line along x
+    block = [(20.0, -1.0), (23.0, -1.0), (23.0, 1.0), (20.0, 1.0)]                        # sits on the path
+    far = [(60.0, 30.0), (62.0, 30.0), (62.0, 32.0), (60.0, 32.0)]
+    polys = [block, far]
+    stc = np.zeros(cfg.Nstcobs * cfg.nstcobs)
+    fh = O.FleetHost(cfg, np.zeros((1, 3)), np.array([[90.0, 0.0, 0.0]]), ref[None], [len(ref)], stc, tuning, base,
+                     mc.low_speed, dyn_cur=np.array([[[40.0, 0.5]]]), dyn_disp=np.zeros((1, 1, 2)))
+    fh.hint, fh.use_hint = np.zeros((1, N, 2)), np.zeros(1, np.int32)
+    fh.sw_state = np.zeros((1, 2), np.int32)
+    fh.sw_poly_xy = np.array(polys, dtype=np.float64)[None]
+    fh.sw_poly_nv = np.array([[4, 4]], np.int32)
+    sw = _HintSwitcher(10, 2, 10)
+    decisions = []
+    for step in range(260):
+        x = 0.24 * step
+        fh.state[0, :2] = (x, 0.3)
+        fh.idx_ref[0] = max(0, step - 1)
+        O.fleet_pack(fh, True)
+        idx = int(fh.idx_ref[0])
+        original = [ref[min(idx + k, len(ref) - 1)] for k in range(N)]
+        obstacles = polys + [[(40.0 - 1.6, 0.5 - 1.6), (40.0 + 1.6, 0.5 - 1.6), (40.0 + 1.6, 0.5 + 1.6), (40.0 - 1.6, 0.5 + 1.6)]]
+        expect = sw.switch((x, 0.3), original, original, obstacles)
+        assert bool(fh.use_hint[0]) == bool(expect), f"step {step}"
+        assert int(fh.sw_state[0, 0]) == int(sw.switch_on) and int(fh.sw_state[0, 1]) == sw.detach_cnt
+        decisions.append(int(expect))
+    d = np.array(decisions)
+    assert d[0] == 0 and d.max() == 1 and d[-1] == 0 and (np.diff(d) != 0).sum() >= 2   # off -> on -> ... -> off

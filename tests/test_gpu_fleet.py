@@ -107,3 +107,45 @@ def test_pack_with_dqn_hint_bit_exact():
     p_plain = O.fleet_pack(fh, use_libm=False)
     assert np.array_equal(refs[:, 2], p_plain[e, off["r"]:off["r"] + 3 * N].reshape(N, 3)[:, 2])
     assert np.array_equal(p_dev[e, 3:5], rl.cpu().numpy()[e, -1]) and p_dev[e, 5] == p_plain[e, 5]
+
+
+def test_hint_switch_on_device_matches_oracle():
+    """HintSwitcher evaluated inside the pack kernel: decision, its state and the packed vector
+    equal the oracle's over several closed-loop steps."""
+    import torch
+    n = 48
+    mc = t.Configurator()
+    fl = t.scenes.make_fleet(n, seed=17)
+    # move the first rectangle of every robot onto its path so that the switch has something to see
+    for i in range(n):
+        (ax, ay), (bx, by) = fl["paths"][i][0], fl["paths"][i][1]
+        cx, cy = ax + 0.35 * (bx - ax), ay + 0.35 * (by - ay)
+        fl["static_polys"][i][0] = [(cx - 0.6, cy - 0.6), (cx + 0.6, cy - 0.6), (cx + 0.6, cy + 0.6), (cx - 0.6, cy + 0.6)]
+    fp = t.FleetPlanner(mc, fl["init"], fl["goal"], fl["paths"], mode="work", max_inner_iterations=40, max_outer_iterations=3)
+    fp.update_static_constraints(fl["static_polys"], per_robot=True)
+    fp.set_moving_obstacles(fl["moving_pos"], fl["moving_disp"])
+    fp.enable_hint_switch(fl["static_polys"], per_robot=True)
+    tuning, base = work_mode(mc, "work")
+    fh = O.FleetHost(fp.cfg, fl["init"], fl["goal"], fp.ref_traj.cpu().numpy(), fp.ref_len.cpu().numpy(),
+                     fp.stc.cpu().numpy(), tuning, base, mc.low_speed, dyn_cur=fl["moving_pos"], dyn_disp=fl["moving_disp"])
+    fh.sw_state = np.zeros((n, 2), np.int32)
+    fh.sw_poly_xy, fh.sw_poly_nv = fp.sw_poly_xy.cpu().numpy(), fp.sw_poly_nv.cpu().numpy()
+    fh.use_hint = np.zeros(n, np.int32)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    seen_on = 0
+    for k in range(4):
+        agent5 = torch.cat([fp.state, fp.last_u], 1).contiguous()
+        act = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32).cuda()
+        rl = t.dqn.rl_ref_device(agent5, act)
+        fp.set_hint(rl, fp.use_hint)
+        fh.hint = rl.cpu().numpy()
+        fp.step(); torch.cuda.synchronize()
+        p = O.fleet_pack(fh, use_libm=False)
+        assert np.array_equal(fp.use_hint.cpu().numpy(), fh.use_hint), f"switch decision differs at step {k}"
+        assert np.array_equal(fp.sw_state.cpu().numpy(), fh.sw_state)
+        assert np.array_equal(fp.p.cpu().numpy(), p)
+        ref = O.solve_batch(fp.cfg, p, threads=8, warp=True)
+        O.fleet_advance(fh, ref["u"], ref["exit_status"], use_libm=False)
+        assert np.array_equal(fp.state.cpu().numpy(), fh.state)
+        seen_on += int(fh.use_hint.sum())
+    assert seen_on > 0

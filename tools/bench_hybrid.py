@@ -5,8 +5,8 @@
   -> pack (hint as reference positions) -> NMPC solve -> advance
 
 all device-resident (ttdqn_internal_obs_device, ttdqn_observe_act_device, ttdqn_rl_ref_device,
-ttmpc_fleet_step_device).  The hint is always on (main.py's HintSwitcher is host-side geometry and
-not part of this build).  python tools/bench_hybrid.py [n=16384] [steps=10]
+ttmpc_fleet_step_device); whether the hint is used is decided per step and environment by the
+HintSwitcher logic inside the pack kernel.  python tools/bench_hybrid.py [n=16384] [steps=10]
 """
 import json
 import os
@@ -50,9 +50,10 @@ def main():
     internal = torch.empty(n, 14, dtype=torch.float32, device="cuda")
     progress = torch.empty(n, dtype=torch.float64, device="cuda")
     rl = torch.empty(n, fp.N, 2, dtype=torch.float64, device="cuda")
-    use = torch.ones(n, dtype=torch.int32, device="cuda")
+    use = torch.zeros(n, dtype=torch.int32, device="cuda")
     agent5 = torch.empty(n, 5, dtype=torch.float64, device="cuda")
     fp.set_hint(rl, use)
+    fp.enable_hint_switch(fl["static_polys"], per_robot=True)      # HintSwitcher(10, 2, 10), main.py:129
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def one_step(times=None):
@@ -79,7 +80,8 @@ def main():
                step_ms_p90=float(np.quantile(tt[:, 0], 0.9)), dqn_part_ms_p50=float(np.median(tt[:, 1])),
                env_steps_per_s=n / (float(np.median(tt[:, 0])) * 1e-3),
                actions_hist=np.bincount(out["action"].cpu().numpy(), minlength=9).tolist(),
-               running=int((fp.status == 0).sum()), mean_inner_iters=float(fp.inner.float().mean()))
+               running=int((fp.status == 0).sum()), mean_inner_iters=float(fp.inner.float().mean()),
+               hint_on=int(fp.use_hint.sum()))
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "bench_hybrid.json"), "a") as f:

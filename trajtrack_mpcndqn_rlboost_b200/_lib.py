@@ -71,6 +71,9 @@ class TtmpcFleet(C.Structure):
         ("base_speed", C.c_double), ("low_speed", C.c_double),
         ("stc_weight", C.c_double), ("dyn_weight", C.c_double),
         ("hint", C.c_void_p), ("use_hint", C.c_void_p),
+        ("sw_state", C.c_void_p), ("sw_poly_xy", C.c_void_p), ("sw_poly_nv", C.c_void_p),
+        ("sw_max_poly", C.c_int), ("sw_max_pv", C.c_int), ("sw_poly_shared", C.c_int), ("sw_detach_steps", C.c_int),
+        ("sw_switch_distance", C.c_double), ("sw_detach_distance", C.c_double), ("sw_dyn_radius", C.c_double),
     ]
 
 

@@ -15,6 +15,62 @@ namespace ttmpc {
 
 __device__ __forceinline__ double hyp2(double dx, double dy) { return sqrt(fma(dx, dx, dy * dy)); }
 
+// shapely Polygon.contains(Point) (strictly inside, even-odd rule) / Polygon.distance(Point)
+__device__ __forceinline__ bool poly_contains(const double *xy, int nv, double px, double py) {
+  bool in = false;
+  for (int i = 0, j = nv - 1; i < nv; j = i++) {
+    const double xi = xy[2 * i], yi = xy[2 * i + 1], xj = xy[2 * j], yj = xy[2 * j + 1];
+    if (((yi > py) != (yj > py)) && (px < (xj - xi) * (py - yi) / (yj - yi) + xi)) in = !in;
+  }
+  return in;
+}
+__device__ __forceinline__ double poly_distance(const double *xy, int nv, double px, double py) {
+  if (poly_contains(xy, nv, px, py)) return 0.0;
+  double best = INFINITY;
+  for (int i = 0, j = nv - 1; i < nv; j = i++) {
+    const double ax = xy[2 * j], ay = xy[2 * j + 1], dx = xy[2 * i] - ax, dy = xy[2 * i + 1] - ay;
+    const double len2 = dx * dx + dy * dy;
+    double t = 0.0;
+    if (len2 > 0.0) { t = ((px - ax) * dx + (py - ay) * dy) / len2; t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); }
+    const double qx = ax + t * dx - px, qy = ay + t * dy - py;
+    const double d = sqrt(qx * qx + qy * qy);
+    if (d < best) best = d;
+  }
+  return best;
+}
+// HintSwitcher.switch (main_pre.py:35-52) of robot e, on the ORIGINAL local reference
+__device__ int hint_switch(const ttmpc_fleet &f, int e, int N, const double *ref, int L, int idx) {
+  int *st = f.sw_state + 2 * e;  // switch_on, detach_cnt
+  const double px = f.state[3 * e], py = f.state[3 * e + 1];
+  const int n_stc = f.sw_poly_xy ? f.sw_max_poly : 0, n_dyn = f.dyn_cur ? f.n_dyn_live : 0;
+  const double *pxy = f.sw_poly_xy ? f.sw_poly_xy + (f.sw_poly_shared ? 0 : (size_t)e * f.sw_max_poly * f.sw_max_pv * 2) : nullptr;
+  const int *pnv = f.sw_poly_nv ? f.sw_poly_nv + (f.sw_poly_shared ? 0 : (size_t)e * f.sw_max_poly) : nullptr;
+  bool cnt_flag = false;
+  for (int k = 0; k < N; k++) {
+    int r = idx + k; if (r > L - 1) r = L - 1;
+    const double ox = ref[3 * r], oy = ref[3 * r + 1];
+    for (int o = 0; o < n_stc + n_dyn; o++) {
+      double rect[8];
+      const double *xy; int nv;
+      if (o < n_stc) { nv = pnv[o]; xy = pxy + (size_t)o * f.sw_max_pv * 2; if (nv < 3) continue; }
+      else {  // circle_to_rect (main.py:91-95)
+        const double *c = f.dyn_cur + ((size_t)e * f.n_dyn_live + (o - n_stc)) * 2, rr = f.sw_dyn_radius;
+        rect[0] = c[0] - rr; rect[1] = c[1] - rr; rect[2] = c[0] + rr; rect[3] = c[1] - rr;
+        rect[4] = c[0] + rr; rect[5] = c[1] + rr; rect[6] = c[0] - rr; rect[7] = c[1] + rr;
+        xy = rect; nv = 4;
+      }
+      const double dist = poly_distance(xy, nv, px, py);
+      if (poly_contains(xy, nv, ox, oy)) {
+        if (dist < f.sw_switch_distance && !st[0]) { st[0] = 1; return 1; }
+      } else if (dist > f.sw_detach_distance && st[0]) {
+        if (st[1] > f.sw_detach_steps) { st[0] = 0; st[1] = 0; }
+        else if (!cnt_flag) { st[1] += 1; cnt_flag = true; }
+      }
+    }
+  }
+  return st[0];
+}
+
 // One CTA per robot.  Thread 0 does the scalar decisions (closest reference point, goal test,
 // speed reference); all threads then write the packed vector, element o of the row by thread
 // o mod blockDim (coalesced 8-byte stores).
@@ -22,7 +78,7 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
                                                          double *__restrict__ p_all) {
   const int e = blockIdx.x;
   if (e >= f.n) return;
-  __shared__ int s_idx;
+  __shared__ int s_idx, s_hint;
   __shared__ double s_speed;
   const double *st = f.state + 3 * e, *goal = f.goal + 3 * e, *lu = f.last_u + 2 * e;
   const double *ref = f.ref_traj + (size_t)e * f.ref_stride * 3;
@@ -30,6 +86,7 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
   if (threadIdx.x == 0) {
     int idx = f.idx_ref[e];
     const double x = st[0], y = st[1];
+    const bool was_running = f.status[e] == TTMPC_FLEET_RUNNING;
     if (f.status[e] == TTMPC_FLEET_RUNNING) {
       // get_local_ref_traj (trajectory_generator.py:214-219): first minimum in the window
       int lo = idx - 1 * f.action_steps; if (lo < 0) lo = 0;
@@ -46,6 +103,9 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
       if (close && fabs(lu[0]) < 0.05) f.status[e] = TTMPC_FLEET_REACHED;
     }
     s_idx = idx;
+    // hybrid mode: main.py:200 evaluates the switch before get_action's goal test
+    if (f.sw_state && f.hint && f.use_hint && was_running) f.use_hint[e] = hint_switch(f, e, N, ref, L, idx);
+    s_hint = (f.hint && f.use_hint && f.use_hint[e]) ? 1 : 0;
     // speed reference (:248-255)
     const double dist = hyp2(x - goal[0], y - goal[1]);
     double v = f.base_speed;
@@ -61,7 +121,7 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
   const int o_refs = 18, o_speed = o_refs + 3 * N, o_other = o_speed + N, o_stc = o_other + d.n_other,
             o_dyn = o_stc + d.n_stc, o_ws = o_dyn + d.n_dyn, o_wd = o_ws + N;
   const double *stc = f.stc + (f.stc_shared ? 0 : (size_t)e * d.n_stc);
-  const bool hinted = f.hint && f.use_hint && f.use_hint[e];  // hybrid mode: DQN hint positions
+  const bool hinted = s_hint != 0;  // hybrid mode: DQN hint positions
   const double *hint = f.hint + (size_t)e * N * 2;
   for (int o = threadIdx.x; o < d.np; o += blockDim.x) {
     double v;

@@ -123,6 +123,31 @@ class FleetPlanner:
         use_hint [n] int32 -- where non-zero the hint replaces the reference positions."""
         self.hint, self.use_hint = rl_ref, use_hint
 
+    def enable_hint_switch(self, polygons, per_robot: bool = False, max_switch_distance: float = 10.0,
+                           min_detach_distance: float = 2.0, min_detach_steps: int = 10):
+        """Let the pack kernel decide per step whether the DQN hint is used, as
+        ``HintSwitcher(10, 2, 10).switch(...)`` does in main.py:129,200 (main_pre.py:27-52).
+        polygons: the processed (inflated) static obstacle polygons, shared or one list per robot;
+        moving obstacles enter as circle_to_rect squares of radius DYN_OBS_SIZE."""
+        t = self.torch
+        lists = polygons if per_robot else [polygons]
+        max_poly = max(1, max(len(pl) for pl in lists))
+        max_pv = max(3, max((len(poly) for pl in lists for poly in pl), default=3))
+        xy = np.zeros((len(lists), max_poly, max_pv, 2))
+        nv = np.zeros((len(lists), max_poly), np.int32)
+        for i, pl in enumerate(lists):
+            for j, poly in enumerate(pl):
+                a = np.asarray(poly, np.float64).reshape(-1, 2)
+                xy[i, j, :len(a)] = a
+                nv[i, j] = len(a)
+        dev = self.state.device
+        self.sw_poly_xy, self.sw_poly_nv = t.tensor(xy, device=dev), t.tensor(nv, device=dev)
+        self.sw_shape = (max_poly, max_pv, 0 if per_robot else 1)
+        self.sw_params = (float(max_switch_distance), float(min_detach_distance), int(min_detach_steps))
+        self.sw_state = t.zeros(self.n, 2, dtype=t.int32, device=dev)
+        if self.use_hint is None:
+            self.use_hint = t.zeros(self.n, dtype=t.int32, device=dev)
+
     # ------------------------------------------------------------------ the step
     def _fleet_struct(self) -> _lib.TtmpcFleet:
         f = _lib.TtmpcFleet()
@@ -143,6 +168,12 @@ class FleetPlanner:
         f.stc_weight, f.dyn_weight = self.stc_weight, self.dyn_weight
         if self.hint is not None and self.use_hint is not None:
             f.hint, f.use_hint = self.hint.data_ptr(), self.use_hint.data_ptr()
+        if getattr(self, "sw_state", None) is not None:
+            f.sw_state = self.sw_state.data_ptr()
+            f.sw_poly_xy, f.sw_poly_nv = self.sw_poly_xy.data_ptr(), self.sw_poly_nv.data_ptr()
+            f.sw_max_poly, f.sw_max_pv, f.sw_poly_shared = self.sw_shape
+            f.sw_switch_distance, f.sw_detach_distance, f.sw_detach_steps = self.sw_params
+            f.sw_dyn_radius = DYN_OBS_SIZE
         return f
 
     def _result_struct(self) -> _lib.TtmpcResult:
