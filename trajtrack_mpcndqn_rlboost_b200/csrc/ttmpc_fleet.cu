@@ -38,7 +38,40 @@ __device__ __forceinline__ double poly_distance(const double *xy, int nv, double
   }
   return best;
 }
-// HintSwitcher.switch (main_pre.py:35-52) of robot e, on the ORIGINAL local reference
+constexpr int SW_MAX_OBS = 64;  // obstacles per robot the parallel switch path handles (more: serial path)
+// obstacle o of robot e in the list "static polygons + circle_to_rect(moving obstacle)"; rect: 8 doubles scratch
+__device__ __forceinline__ const double *sw_obstacle(const ttmpc_fleet &f, int e, int o, int n_stc, double *rect, int *nv) {
+  if (o < n_stc) {
+    const double *pxy = f.sw_poly_xy + (f.sw_poly_shared ? 0 : (size_t)e * f.sw_max_poly * f.sw_max_pv * 2);
+    const int *pnv = f.sw_poly_nv + (f.sw_poly_shared ? 0 : (size_t)e * f.sw_max_poly);
+    *nv = pnv[o];
+    return pxy + (size_t)o * f.sw_max_pv * 2;
+  }
+  const double *c = f.dyn_cur + ((size_t)e * f.n_dyn_live + (o - n_stc)) * 2, rr = f.sw_dyn_radius;  // main.py:91-95
+  rect[0] = c[0] - rr; rect[1] = c[1] - rr; rect[2] = c[0] + rr; rect[3] = c[1] - rr;
+  rect[4] = c[0] + rr; rect[5] = c[1] + rr; rect[6] = c[0] - rr; rect[7] = c[1] + rr;
+  *nv = 4;
+  return rect;
+}
+// the state machine of HintSwitcher.switch on precomputed predicates: dist[o] (distance of the
+// robot to obstacle o, < 0: unused slot) and in[k * n_obs + o] (reference point k inside obstacle o)
+__device__ int hint_switch_sm(const ttmpc_fleet &f, int e, int N, int n_obs, const double *dist,
+                              const unsigned char *in) {
+  int *st = f.sw_state + 2 * e;
+  bool cnt_flag = false;
+  for (int k = 0; k < N; k++)
+    for (int o = 0; o < n_obs; o++) {
+      if (dist[o] < 0.0) continue;
+      if (in[k * n_obs + o]) {
+        if (dist[o] < f.sw_switch_distance && !st[0]) { st[0] = 1; return 1; }
+      } else if (dist[o] > f.sw_detach_distance && st[0]) {
+        if (st[1] > f.sw_detach_steps) { st[0] = 0; st[1] = 0; }
+        else if (!cnt_flag) { st[1] += 1; cnt_flag = true; }
+      }
+    }
+  return st[0];
+}
+// HintSwitcher.switch (main_pre.py:35-52) of robot e, on the ORIGINAL local reference (serial form)
 __device__ int hint_switch(const ttmpc_fleet &f, int e, int N, const double *ref, int L, int idx) {
   int *st = f.sw_state + 2 * e;  // switch_on, detach_cnt
   const double px = f.state[3 * e], py = f.state[3 * e + 1];
@@ -78,8 +111,10 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
                                                          double *__restrict__ p_all) {
   const int e = blockIdx.x;
   if (e >= f.n) return;
-  __shared__ int s_idx, s_hint;
+  __shared__ int s_idx, s_hint, s_sw;
   __shared__ double s_speed;
+  __shared__ double s_dist[SW_MAX_OBS];
+  __shared__ unsigned char s_in[32 * SW_MAX_OBS];
   const double *st = f.state + 3 * e, *goal = f.goal + 3 * e, *lu = f.last_u + 2 * e;
   const double *ref = f.ref_traj + (size_t)e * f.ref_stride * 3;
   const int L = f.ref_len[e], N = d.N;
@@ -103,9 +138,7 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
       if (close && fabs(lu[0]) < 0.05) f.status[e] = TTMPC_FLEET_REACHED;
     }
     s_idx = idx;
-    // hybrid mode: main.py:200 evaluates the switch before get_action's goal test
-    if (f.sw_state && f.hint && f.use_hint && was_running) f.use_hint[e] = hint_switch(f, e, N, ref, L, idx);
-    s_hint = (f.hint && f.use_hint && f.use_hint[e]) ? 1 : 0;
+    s_sw = (f.sw_state && f.hint && f.use_hint && was_running) ? 1 : 0;
     // speed reference (:248-255)
     const double dist = hyp2(x - goal[0], y - goal[1]);
     double v = f.base_speed;
@@ -117,6 +150,31 @@ __global__ void __launch_bounds__(128) fleet_pack_kernel(const ttmpc_fleet f, co
   }
   __syncthreads();
   const int idx = s_idx;
+  // hybrid mode: main.py:200 evaluates HintSwitcher.switch before get_action's goal test.  The
+  // geometric predicates are independent: one obstacle distance / one (point, obstacle)
+  // containment per thread, then thread 0 walks the state machine over them.
+  if (s_sw) {
+    const int n_stc = f.sw_poly_xy ? f.sw_max_poly : 0, n_obs = n_stc + (f.dyn_cur ? f.n_dyn_live : 0);
+    if (n_obs <= SW_MAX_OBS) {
+      double rect[8]; int nv;
+      for (int o = threadIdx.x; o < n_obs; o += blockDim.x) {
+        const double *xy = sw_obstacle(f, e, o, n_stc, rect, &nv);
+        s_dist[o] = nv < 3 ? -1.0 : poly_distance(xy, nv, st[0], st[1]);
+      }
+      for (int q = threadIdx.x; q < N * n_obs; q += blockDim.x) {
+        const int k = q / n_obs, o = q - k * n_obs;
+        const double *xy = sw_obstacle(f, e, o, n_stc, rect, &nv);
+        int r = idx + k; if (r > L - 1) r = L - 1;
+        s_in[q] = (nv >= 3 && poly_contains(xy, nv, ref[3 * r], ref[3 * r + 1])) ? 1 : 0;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) f.use_hint[e] = hint_switch_sm(f, e, N, n_obs, s_dist, s_in);
+    } else if (threadIdx.x == 0) {
+      f.use_hint[e] = hint_switch(f, e, N, ref, L, idx);
+    }
+  }
+  if (threadIdx.x == 0) s_hint = (f.hint && f.use_hint && f.use_hint[e]) ? 1 : 0;
+  __syncthreads();
   double *p = p_all + (size_t)e * d.np;
   const int o_refs = 18, o_speed = o_refs + 3 * N, o_other = o_speed + N, o_stc = o_other + d.n_other,
             o_dyn = o_stc + d.n_stc, o_ws = o_dyn + d.n_dyn, o_wd = o_ws + N;
