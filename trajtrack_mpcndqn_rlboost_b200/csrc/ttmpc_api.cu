@@ -240,6 +240,8 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   A.dyn_scratch = w->dyn_scratch; A.work_counter = w->work_counter; A.stats = w->stats;
   A.run_stats = w->stats + 18;  // stats block: [18] evaluations, [19] count of finished scenes
   { const char *ne = std::getenv("TTMPC_NO_EARLY_HELP"); if (ne && ne[0] == '1') A.run_stats = nullptr; }
+  // the running average behind the early-helper threshold is per launch (workloads differ by 30x)
+  if (A.run_stats) CUDA_TRY(cudaMemsetAsync(A.run_stats, 0, 2 * sizeof(unsigned long long), st));
   A.n_scenes = n_scenes; A.use_u0 = use_u0; A.use_y0 = use_y0;
   // more scenes than resident warps: dispatch the likely-long ones first.  Not on the streamed
   // host path (scenes become available in index order there).  TTMPC_NO_ORDER=1 disables it.
