@@ -51,6 +51,25 @@ def eval_flops(cfg, grad: bool, bodies_per_eval: float) -> float:
 
 
 def clocks_sampler(stop, out, gpu_index):
+    """Sample SM clock, power and throttle reasons during the timed region: NVML every 10 ms when
+    pynvml is importable, else nvidia-smi (the recipe's clocks line) every 200 ms."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not stop.is_set():
+            r = get_reasons(h)
+            act = lambda k: "Active" if (r & bits[k]) else "Not Active"
+            out.append([str(gpu_index), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                        str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0), hex(r), act("hw_slowdown"),
+                        act("hw_thermal_slowdown"), act("sw_thermal_slowdown"), act("sw_power_cap")])
+            stop.wait(0.01)
+        return
+    except Exception:
+        pass
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
