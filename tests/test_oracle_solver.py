@@ -93,3 +93,26 @@ def test_ragged_batches(cfg):
     assert np.array_equal(one["u"][0], three["u"][0])
     empty = O.solve_batch(cfg, p[:0], warp=True)
     assert empty["u"].shape == (0, 40)
+
+
+def test_converged_solutions_are_local_minimisers_for_an_independent_optimizer(cfg):
+    """PANOC + ALM here is restated from the published algorithm (unpinned against OpEn itself).
+    Independent check: on converged scenes scipy's L-BFGS-B, started at the returned u on the same
+    inner problem psi(.; c, y) (psi is pinned to the reference's goldens), can only lower psi by
+    what the stopping rule |gamma fpr| < 1e-4 (gamma ~ 1e-3) leaves on the table and stays close."""
+    from scipy.optimize import minimize
+    p = t.scenes.make_scenes(48, cfg, seed=5, n_static=4, n_dynamic=3)
+    out = O.solve_batch(cfg, p, threads=4)
+    N = cfg.N_hor
+    lo = np.tile([cfg.lin_vel_min, -cfg.ang_vel_max], N)
+    hi = np.tile([cfg.lin_vel_max, cfg.ang_vel_max], N)
+    conv = np.where(out["exit_status"] == 0)[0][:12]
+    assert len(conv) >= 8
+    for i in conv:
+        u, y, c = out["u"][i], out["y"][i], out["pen"][i]
+        f = lambda x: O.psi(cfg, x, p[i], c, y)
+        g = lambda x: O.psi_grad(cfg, x, p[i], c, y)
+        r = minimize(f, u, jac=g, method="L-BFGS-B", bounds=list(zip(lo, hi)),
+                     options=dict(maxiter=2000, ftol=1e-15, gtol=1e-10))
+        assert f(u) - r.fun <= 5e-3 * max(1.0, abs(f(u))), (i, f(u), r.fun)
+        assert np.abs(r.x - u).max() <= 0.1, (i, np.abs(r.x - u).max())
