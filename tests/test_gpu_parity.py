@@ -126,6 +126,24 @@ def test_other_horizons_and_obstacle_counts(cfg):
         assert_parity(sol, ref, 40)
 
 
+def test_large_shapes_and_limits(cfg):
+    """A large configuration that still fits one SM (horizon 32, 20 static and 30 dynamic slots,
+    L-BFGS memory 16) and every per-dimension maximum at once (the API then packs fewer scenes
+    per CTA): bit-exact like the others."""
+    mc = t.Configurator(N_hor=32, Nstcobs=20, Ndynobs=30, Nother=10)
+    c = mc.to_ttmpc(lbfgs_memory=16)
+    p = t.scenes.make_scenes(24, c, seed=77, n_static=6, n_dynamic=5)
+    sol = t.BatchSolver(c).run(p)
+    ref = O.solve_batch(c, p, threads=os.cpu_count(), warp=True)
+    assert_parity(sol, ref, 24)
+    # every per-dimension maximum at once: 60 KB of tables per scene, so fewer scenes per CTA
+    big = t.Configurator(N_hor=32, Nstcobs=32, Ndynobs=64, Nother=32).to_ttmpc(lbfgs_memory=16)
+    pb = t.scenes.make_scenes(12, big, seed=78, n_static=8, n_dynamic=10)
+    solb = t.BatchSolver(big).run(pb)
+    refb = O.solve_batch(big, pb, threads=os.cpu_count(), warp=True)
+    assert_parity(solb, refb, 12)
+
+
 def test_ragged_and_empty_batches(cfg, solver):
     p = t.scenes.make_scenes(5, cfg, seed=23, n_static=3, n_dynamic=1)
     full = solver.run(p)

@@ -85,8 +85,18 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   g->off_od = g->off_os + c->Nstcobs * c->nstcobs;
   g->off_qdyn = g->off_od + c->Ndynobs * c->ndynobs * N + N;
   g->np = g->off_qdyn + N;
-  g->warps_per_block = 4;
   g->smem_per_warp = smem_bytes_per_warp(N, g->Nother, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
+  {
+    // 4 scenes per CTA when they fit the 227 KB a CTA can opt in to (3 CTAs per SM for the default
+    // shapes), fewer for large configurations; one scene must fit
+    const size_t cap = 232448 - 256;
+    if ((size_t)g->smem_per_warp > cap)
+      return fail(TTMPC_ERR_UNSUPPORTED, "configuration does not fit in shared memory: " +
+                  std::to_string(g->smem_per_warp) + " bytes of tables per scene, 227 KB per SM");
+    int wpb = 4;
+    while (wpb > 1 && (size_t)g->smem_per_warp * wpb > cap) wpb--;
+    g->warps_per_block = wpb;
+  }
   g->ts = c->ts; g->inv_ts = 1.0 / c->ts; g->h6 = c->ts / 6.0; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;
   g->vmin = c->lin_vel_min; g->vmax = c->lin_vel_max; g->wmax = c->ang_vel_max;
   g->amin = c->lin_acc_min; g->amax = c->lin_acc_max; g->awmax = c->ang_acc_max;
