@@ -129,12 +129,15 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
   for (int base = 0; base < K; base += 32) {
     const int j = base + lane;
     if (j < K) {
+      // one call for all three kinds of product (a divergent call would run three times)
       const int l = 1 + j / 3, kind = j - 3 * (l - 1);
       const int pl = lb_slot<DM>(g, U, l);
-      if (kind == 0)      sm.gsy[k0 * M1 + pl] = row_dot(sm.lbs + k0 * NP, sm.lby + pl * NP, N);
-      else if (kind == 1) sm.gsy[pl * M1 + k0] = row_dot(sm.lbs + pl * NP, sm.lby + k0 * NP, N);
-      else { const double v = row_dot(sm.lby + k0 * NP, sm.lby + pl * NP, N);
-             sm.gyy[k0 * M1 + pl] = v; sm.gyy[pl * M1 + k0] = v; }
+      const double2 *ra = kind == 0 ? sm.lbs + k0 * NP : kind == 1 ? sm.lbs + pl * NP : sm.lby + k0 * NP;
+      const double2 *rb = kind == 1 ? sm.lby + k0 * NP : sm.lby + pl * NP;
+      const double v = row_dot(ra, rb, N);
+      double *dst = kind == 0 ? sm.gsy + k0 * M1 + pl : kind == 1 ? sm.gsy + pl * M1 + k0 : sm.gyy + k0 * M1 + pl;
+      *dst = v;
+      if (kind == 2) sm.gyy[pl * M1 + k0] = v;
     }
   }
   __syncwarp();
