@@ -255,8 +255,8 @@ def main():
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch on this
-                # workload, ncu --set full capture profiles/r1_e_solve_kernel_final.txt
-                "traffic": 145.7e6 if args.workload == "static4096" else None,
+                # workload, ncu --set full capture profiles/r1_f_solve_kernel_final.txt
+                "traffic": 144.6e6 if args.workload == "static4096" else None,
                 "peak_source": "measured live: DFMA probe kernel (ttmpc_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "hbm_GBps_algorithmic": (p_host.nbytes + d2h) / (local_ms * 1e-3) / 1e9,
