@@ -287,12 +287,14 @@ __device__ __forceinline__ double &dynf(double *t, const DevCfg &g, int f, int j
   return t[((size_t)f * g.Ndyn + j) * g.N + k];
 }
 
-__device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const double *p,
+// Staging, part 1: everything before the dynamic-obstacle block.  `p` points at a copy of the
+// row prefix [0, off_od) (shared-memory copy made by the bulk copy below, or the row itself).
+__device__ inline void stage_part1(const DevCfg &g, const WarpSmem &sm, const double *p, const double *p_global,
                                    double *dyn_scratch, int lane) {
   WarpCtx *c = sm.ctx;
   if (lane == 0) {
     const double *s = p + g.off_s, *q = p + g.off_q;
-    c->p = p; c->dyn = dyn_scratch;
+    c->p = p_global; c->dyn = dyn_scratch;
     c->x0 = s[0]; c->y0 = s[1]; c->th0 = s[2];
     c->xg = s[3]; c->yg = s[4]; c->thg = s[5];
     c->v_init = s[6]; c->w_init = s[7];
@@ -347,19 +349,46 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
   const double *cpar = p + g.off_c;
   for (int t = lane; t < g.Nother * g.N; t += 32)
     sm.fleet[t] = make_float2((float)cpar[(size_t)t * 3], (float)cpar[(size_t)t * 3 + 1]);
+  // contact needs |p - o|^2 < d^2; the fp32 prefilter pads d by the worst rounding of the
+  // fp32 copies (8 ulp_f32 of the largest coordinate of this scene) so it never rejects a contact
+  double cmax = 0.0;
+  bool cnan = false;
+  for (int t = lane; t < g.Nother * g.N; t += 32) {
+    const double ax = fabs(cpar[(size_t)t * 3]), ay = fabs(cpar[(size_t)t * 3 + 1]);
+    cnan = cnan || !(ax == ax) || !(ay == ay);
+    cmax = fmax(cmax, fmax(ax, ay));
+  }
+  for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(FULL, cmax, o));
+  cnan = __any_sync(FULL, cnan);
   if (lane == 0) {
-    // contact needs |p - o|^2 < d^2; the fp32 prefilter pads d by the worst rounding of the
-    // fp32 copies (8 ulp_f32 of the largest coordinate of this scene) so it never rejects a contact
-    double cmax = 0.0;
-    for (int t = 0; t < g.Nother * g.N; t++)
-      cmax = fmax(cmax, fmax(fabs(cpar[(size_t)t * 3]), fabs(cpar[(size_t)t * 3 + 1])));
+    if (cnan) cmax = NAN;
     const double d = sqrt(g.veh_d2), pad = 4.8e-7 * (2.0 * cmax + 2.0 * d + 1.0) + 1e-6;
     float thr = __double2float_ru((d + pad) * (d + pad) * (1.0 + 1e-6));
     if (!(cmax == cmax)) thr = INFINITY;  // NaN coordinates: let the exact test decide
     c->fleet_thr = thr;
   }
-  // dynamic obstacle table
-  const double *od = p + g.off_od, *qdyn = p + g.off_qdyn;
+  // live mask of the box-guarded compaction, other robots (NaN / inf coordinates stay live)
+  {
+    const double x0 = p[g.off_s], y0 = p[g.off_s + 1];
+    const double vm = fmax(fabs(g.vmax), fabs(g.vmin));
+    const double bh = 2.0 * g.N * g.ts * vm + 1.0;
+    unsigned fl = 0;
+    const double dveh = sqrt(g.veh_d2) * 1.001 + 1e-3;
+    for (int t = lane; t < g.Nother * g.N; t += 32) {
+      const int j = t / g.N;
+      const bool outside = fabs(cpar[(size_t)t * 3] - x0) > bh + dveh || fabs(cpar[(size_t)t * 3 + 1] - y0) > bh + dveh;
+      if (!outside) fl |= 1u << j;
+    }
+    fl = __reduce_or_sync(FULL, fl);
+    if (lane == 0) { c->box_half = bh; c->fleet_live = fl; }
+  }
+  __syncwarp();
+}
+
+// Staging, part 2: the dynamic-obstacle table.  od = the o_d block, qdyn = the q_dyn block.
+__device__ inline void stage_part2(const DevCfg &g, const WarpSmem &sm, const double *od, const double *qdyn,
+                                   double *dyn_scratch, int lane) {
+  WarpCtx *c = sm.ctx;
   const int npair = g.Ndyn * g.N;
   for (int t = lane; t < npair; t += 32) {
     int j = t / g.N, k = t - j * g.N;
@@ -391,11 +420,10 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
       sm.dynb[3 * t] = (float)cx; sm.dynb[3 * t + 1] = (float)cy; sm.dynb[3 * t + 2] = r2f;
     }
   }
-  // live masks of the box-guarded compaction (NaN / inf coordinates stay live)
+  // live mask of the box-guarded compaction, dynamic obstacles (NaN / inf coordinates stay live)
   {
-    const double x0 = p[g.off_s], y0 = p[g.off_s + 1];
-    const double vm = fmax(fabs(g.vmax), fabs(g.vmin));
-    const double bh = 2.0 * g.N * g.ts * vm + 1.0;
+    const double x0 = c->x0, y0 = c->y0;
+    const double bh = c->box_half;
     unsigned long long dl = 0;
     for (int t = lane; t < npair; t += 32) {
       const int j = t / g.N;
@@ -405,18 +433,29 @@ __device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const do
       const bool outside = fabs(e[0] - x0) > bh + rmax || fabs(e[1] - y0) > bh + rmax;
       if (!outside) dl |= 1ull << j;
     }
-    unsigned fl = 0;
-    const double dveh = sqrt(g.veh_d2) * 1.001 + 1e-3;
-    for (int t = lane; t < g.Nother * g.N; t += 32) {
-      const int j = t / g.N;
-      const bool outside = fabs(cpar[(size_t)t * 3] - x0) > bh + dveh || fabs(cpar[(size_t)t * 3 + 1] - y0) > bh + dveh;
-      if (!outside) fl |= 1u << j;
-    }
     const unsigned dlo = __reduce_or_sync(FULL, (unsigned)dl), dhi = __reduce_or_sync(FULL, (unsigned)(dl >> 32));
-    fl = __reduce_or_sync(FULL, fl);
-    if (lane == 0) { c->box_half = bh; c->dyn_live = ((unsigned long long)dhi << 32) | dlo; c->fleet_live = fl; }
+    if (lane == 0) c->dyn_live = ((unsigned long long)dhi << 32) | dlo;
   }
   __syncwarp();
+}
+
+// Staging = part 1 + part 2, straight from the scene's row of the parameter block (read once;
+// ~35 us per scene, 1 % of an average solve: measured with -DTTMPC_PROFILE_STAGE, tools/stage_profile.py).
+// A cp.async.bulk landing zone in the (then empty) L-BFGS ring was tried and dropped: part 2 is
+// bound by its 300 sincos + 1200 divisions, not by the loads, and its 14.4 KB block does not fit the ring.
+__device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const double *p,
+                                   double *dyn_scratch, int lane) {
+#ifdef TTMPC_PROFILE_STAGE
+  const long long td0 = clock64();
+#endif
+  stage_part1(g, sm, p, p, dyn_scratch, lane);
+#ifdef TTMPC_PROFILE_STAGE
+  const long long td1 = clock64();
+#endif
+  stage_part2(g, sm, p + g.off_od, p + g.off_qdyn, dyn_scratch, lane);
+#ifdef TTMPC_PROFILE_STAGE
+  if (lane == 0) { sm.ctx->prof[4] += td1 - td0; sm.ctx->prof[5] += clock64() - td1; }
+#endif
 }
 
 #ifdef TTMPC_PROFILE

@@ -448,6 +448,7 @@ __device__ bool serve_owner(const DevCfg &g, CtaHelp *cta, unsigned char *smem_r
   const WarpSmem own = carve<DM>(base_m, g);
   const int N = g.N;
   unsigned long long t_idle = globaltimer_ns();
+  int idle_polls = 0;
   while (true) {
     int st = 0, alive = 1;
     if (lane == 0) {
@@ -479,14 +480,18 @@ __device__ bool serve_owner(const DevCfg &g, CtaHelp *cta, unsigned char *smem_r
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile int *>(&own.hhdr->state) = 2;
       t_idle = globaltimer_ns();
+      idle_polls = 0;
     } else if (!alive) {
       if (lane == 0) atomicExch(&cta->helper[m], -1);
       return true;
     } else {
-      __nanosleep(32);
-      if (globaltimer_ns() - t_idle > 3000000000ull) {
-        if (lane == 0) atomicExch(&cta->helper[m], -1);
-        return false;
+      // the next request usually follows within a few thousand cycles: poll tightly first
+      if (++idle_polls > 96) {
+        __nanosleep(32);
+        if ((idle_polls & 255) == 0 && globaltimer_ns() - t_idle > 3000000000ull) {
+          if (lane == 0) atomicExch(&cta->helper[m], -1);
+          return false;
+        }
       }
     }
   }
@@ -906,7 +911,12 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
 #endif
     wstats[6] += sm.ctx->prof[2] + sm.ctx->prof[3];
     wstats[7] += clock64() - t_clk0;
+#ifndef TTMPC_PROFILE_STAGE
     sm.ctx->eprof[9] = sm.ctx->prof[3];  // L-BFGS apply alone (slot 6 holds update + apply)
+#else
+    sm.ctx->eprof[9] = 0;
+    sm.ctx->eprof[8] = sm.ctx->prof[4]; sm.ctx->eprof[7] = sm.ctx->prof[5];  // staging part 1 / part 2
+#endif
 #ifdef TTMPC_PROFILE_HELP
     for (int i = 0; i < 4; i++) sm.ctx->eprof[i] = sm.ctx->prof[4 + i];  // helper timeline instead of eval sections
 #endif
@@ -968,7 +978,13 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const __grid_constant__ D
       }
       __threadfence();
     }
+#ifdef TTMPC_PROFILE_STAGE
+    const long long t_stage0 = clock64();
+#endif
     stage_scene(g, sm, A.p + (size_t)scene * g.np, dyn, lane);
+#ifdef TTMPC_PROFILE_STAGE
+    if (lane == 0 && A.eprof) atomicAdd(A.eprof + 9, (unsigned long long)(clock64() - t_stage0));  // staging cycles (slot of the apply timer)
+#endif
     hc.enabled = A.helpers != 0;
     solve_scene<DM, false>(g, sm, A, scene, lane, wstats, hc);
     if (lane == 0) {
