@@ -99,12 +99,13 @@ def summarize_clocks(samples):
             "samples": len(samples)}
 
 
-def build_workload(name, rank, world):
+def build_workload(name, rank, world, batch=0):
     import trajtrack_mpcndqn_rlboost_b200 as t
     w = t.scenes.WORKLOADS[name]
     cfg = t.Configurator().to_ttmpc(**w["solver"])
-    # weak scaling: every rank solves its own shard of n scenes (different seed per rank)
-    p = t.scenes.make_scenes(w["n"], cfg, seed=1000 + rank, n_static=w["n_static"],
+    # weak scaling: every rank solves its own shard of n scenes (different seed per rank);
+    # `batch` numbers the distinct input batches the timed steps rotate through
+    p = t.scenes.make_scenes(w["n"], cfg, seed=1000 + rank + 100 * batch, n_static=w["n_static"],
                              n_dynamic=w["n_dynamic"], blocking_fraction=w["blocking_fraction"])
     return cfg, p, w
 
@@ -153,6 +154,8 @@ def main():
     ap.add_argument("--workload", default="static4096")
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (1 = one at a time)")
+    ap.add_argument("--batches", type=int, default=4, help="distinct input batches the steps rotate through")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -175,14 +178,19 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    cfg, p_host, w = build_workload(args.workload, rank, world)
+    # R distinct input batches rotate through the steps: 4 x 87 MB of parameters > 126 MB of L2, so
+    # no step finds its inputs in L2 (the one-batch-at-a-time leg flushes L2 explicitly as well)
+    R = max(1, args.batches)
+    cfg, p0, w = build_workload(args.workload, rank, world, 0)
+    p_hosts = [p0] + [build_workload(args.workload, rank, world, j)[1] for j in range(1, R)]
+    p_host = p_hosts[0]
     n = len(p_host)
     solver = t.BatchSolver(cfg)
     lib = _lib.load()
     dev = torch.device("cuda", local)
-    p_pinned = torch.from_numpy(p_host).pin_memory()
-    p_dev = p_pinned.to(dev, non_blocking=True)
-    bufs = solver.alloc_device(n, device=dev)
+    p_devs = [torch.from_numpy(p).pin_memory().to(dev, non_blocking=True) for p in p_hosts]
+    D = max(1, args.depth)
+    bufs_ring = [solver.alloc_device(n, device=dev) for _ in range(D)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
 
     def barrier():
@@ -197,50 +205,97 @@ def main():
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return float(tns.item())
 
-    stream = torch.cuda.current_stream()
-    # ---------------- device-resident leg ("value")
-    solver.read_stats(reset=True)
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.warmup + args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.warmup + args.steps)]
-    samples, stop = [], threading.Event()
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    main_stream = torch.cuda.current_stream()
+    # ---------------- one batch at a time ("sequential"): per-batch latency.  Each step is timed by
+    # its own event pair, L2 flushed before it; the next step starts when this one has ended.
+    seq_ms = []
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             barrier()
-            solver.read_stats(reset=True)
-            th.start()
-            t_wall0 = time.perf_counter()
-        flush.zero_()                      # L2 flush between timed iterations
-        ev0[it].record(stream)
-        solver.run_device(p_dev, bufs)     # ONE kernel launch (+ one 4-byte memset)
-        ev1[it].record(stream)
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        solver.run_device(p_devs[it % R], bufs_ring[0])
+        e1.record(main_stream)
+        if it >= args.warmup:
+            seq_ms.append((e0, e1))
+    barrier()
+    seq_ms = [a.elapsed_time(b) for a, b in seq_ms]
+    seq_step_ms = max_over_ranks(sum(seq_ms) / len(seq_ms))
+    # ---------------- device-resident leg ("value"): the same K steps with up to D batches in
+    # flight.  Step i runs on stream i mod D with its own output buffers; the library gives each
+    # stream its own scene queue, so the CTAs of the next batch become resident as the CTAs of
+    # the running one drain and its tail (a few long scenes on an otherwise idle GPU) is filled.
+    # Timed by ONE event pair around all K steps, every step complete at the second event.
+    streams = [torch.cuda.Stream(device=dev) for _ in range(D)]
+
+    def issue(first, count):
+        for it in range(first, first + count):
+            with torch.cuda.stream(streams[it % D]):
+                solver.run_device(p_devs[it % R], bufs_ring[it % D])
+
+    def fork():
+        for s_ in streams:
+            s_.wait_stream(main_stream)
+
+    def join():
+        for s_ in streams:
+            main_stream.wait_stream(s_)
+
+    warm = max(args.warmup, D)  # every stream's scene queue and scratch tables exist before the timed region
+    fork(); issue(0, warm); join()
+    barrier()
+    solver.read_stats(reset=True)
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    th.start()
+    t_wall0 = time.perf_counter()
+    ev_a = torch.cuda.Event(enable_timing=True); ev_b = torch.cuda.Event(enable_timing=True)
+    ev_a.record(main_stream)
+    fork(); issue(warm, args.steps); join()
+    ev_b.record(main_stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     stop.set()
-    kern_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(args.warmup, args.warmup + args.steps)]
+    total_ms = ev_a.elapsed_time(ev_b)
     stats = solver.read_stats(reset=True)
-    step_ms = max_over_ranks(sum(kern_ms) / len(kern_ms))
+    local_ms = total_ms / args.steps
+    step_ms = max_over_ranks(local_ms)
     total_scenes = n * world
     value = total_scenes / (step_ms * 1e-3)
-    status = bufs["exit_status"].cpu().numpy()
+    # exit status of every distinct batch, for the cross-check against the host path below
+    status = []
+    for j in range(R):
+        solver.run_device(p_devs[j], bufs_ring[0]); torch.cuda.synchronize()
+        status.append(bufs_ring[0]["exit_status"].cpu().numpy().copy())
 
     # ---------------- end-to-end leg ("e2e"): the reference-facing call with HOST buffers,
     # BatchSolver.run -> ttmpc_solve_batch_host: host parameters -> pinned staging -> H2D,
-    # solve, D2H of every result field, all inside the timed region.
-    e2e_times = []
-    for it in range(2 + args.steps):
+    # solve, D2H of every result field, all inside the timed region; K calls, up to D in flight
+    # (BatchSolver.run_many: one host thread per in-flight call).
+    host_steps = [p_hosts[it % R] for it in range(args.steps)]
+    solver.run_many(host_steps[:max(2, D)], depth=D)
+    barrier()
+    t0 = time.perf_counter()
+    host_sols = solver.run_many(host_steps, depth=D)
+    e2e_total = time.perf_counter() - t0
+    for it, hs in enumerate(host_sols):
+        assert np.array_equal(hs.exit_status, status[it % R]), "host and device paths disagree"
+    e2e_step = max_over_ranks(e2e_total / args.steps)
+    e2e_value = total_scenes / e2e_step
+    # one call at a time (latency of the blocking call)
+    e2e_seq = []
+    for it in range(2 + min(args.steps, 8)):
         barrier()
         t0 = time.perf_counter()
-        host_sol = solver.run(p_host)
-        dt = time.perf_counter() - t0
+        solver.run(p_hosts[it % R])
         if it >= 2:
-            e2e_times.append(dt)
-    assert np.array_equal(host_sol.exit_status, status)
-    e2e_step = max_over_ranks(sum(e2e_times) / len(e2e_times))
-    e2e_value = total_scenes / e2e_step
+            e2e_seq.append(time.perf_counter() - t0)
+    e2e_seq_step = max_over_ranks(sum(e2e_seq) / len(e2e_seq))
     h2d = p_host.nbytes
     N = cfg.N_hor
     d2h = n * (2 * 2 * N * 8 + 5 * 8 + N * 3 * 8 + 3 * 4 + 4 * 8)
+    exit_hist = np.bincount(np.concatenate(status), minlength=4).tolist()
 
     # ---------------- roofline of the solve kernel: FP64 FMA pipe
     peak = C.c_double()
@@ -250,7 +305,6 @@ def main():
     n_grad = stats["grad_evals"] / steps
     bodies = stats["dyn_bodies"] / max(1.0, (stats["cost_evals"] + stats["grad_evals"]))
     flops = n_cost * eval_flops(cfg, False, bodies) + n_grad * eval_flops(cfg, True, bodies)
-    local_ms = sum(kern_ms) / len(kern_ms)
     achieved = flops / (local_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None,
@@ -286,18 +340,28 @@ def main():
             "config": {"workload": args.workload, "scenes_per_gpu": n, "N_hor": cfg.N_hor,
                        "Nstcobs": cfg.Nstcobs, "Ndynobs": cfg.Ndynobs, "static_per_scene": w["n_static"],
                        "dynamic_per_scene": w["n_dynamic"], "max_inner": cfg.max_inner_iterations,
-                       "max_outer": cfg.max_outer_iterations, "l2": "flushed (256 MB write) between iterations",
+                       "max_outer": cfg.max_outer_iterations,
+                       "pipeline_depth": D,
+                       "inputs": f"{R} distinct resident batches of {p_host.nbytes / 1e6:.0f} MB rotate through the steps "
+                                 f"({R * p_host.nbytes / 1e6:.0f} MB > 126 MB L2): no step finds its inputs in L2",
+                       "timing": "one CUDA-event pair around all K steps (up to pipeline_depth batches in flight, "
+                                 "each on its own stream, all complete at the second event); 'sequential' = one "
+                                 "batch at a time, an event pair per step, L2 flushed by a 256 MB write before each",
                        "parallelism": f"scenes sharded, {world} rank(s), no collective in the solve",
                        "launch": info},
+            # one batch at a time: what a caller that waits for each batch before sending the next sees
+            "sequential": {"value": total_scenes / (seq_step_ms * 1e-3), "ms_per_step": seq_step_ms,
+                           "e2e_value": total_scenes / e2e_seq_step, "e2e_ms_per_step": e2e_seq_step * 1e3},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step * 1e3},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_step * 1e3,
+                    "calls_in_flight": D},
             # per step: solve_kernel, plus rank_scenes_kernel + order_scenes_kernel when the batch
             # is larger than the resident warps (dispatch order)
             "gpu_launches": args.steps * (3 if n > info["grid"] * info["block"] // 32 else 1),
             "clocks": summarize_clocks(samples),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "exit_status_hist": np.bincount(status, minlength=4).tolist(),
+            "exit_status_hist": exit_hist,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)

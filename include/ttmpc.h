@@ -138,6 +138,11 @@ typedef struct ttmpc_result {
  *   use_y0 = 0: multipliers start at zero.  (The reference's Solver object
  *               keeps them between run() calls; the host mirror does that.)
  *   d_c0      : optional per-scene initial penalty (NULL -> cfg value).
+ * Batches in flight: solves issued on the SAME stream run one after the other;
+ * solves issued on DIFFERENT streams (at most 16 per device, each with its own
+ * result buffers) may overlap -- every stream has its own scene queue and scratch
+ * tables inside the library, and the CTAs of the next batch become resident as
+ * the CTAs of the running one drain.  Results do not depend on what else runs.
  * ------------------------------------------------------------------------ */
 int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes,
                              const double *d_p, int use_u0, int use_y0,
@@ -146,7 +151,9 @@ int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes,
 
 /* Same call with HOST buffers: stages p/u/y through pinned memory, launches,
  * copies results back, synchronises.  This is what the python Solver.run
- * mirror and the `e2e` bench leg use.                                     */
+ * mirror and the `e2e` bench leg use.  Thread-safe: calls from several host
+ * threads each take their own staging buffers / streams (8 sets per device, a
+ * ninth caller waits) and overlap on the GPU.                              */
 int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n_scenes,
                            const double *h_p, int use_u0, int use_y0,
                            const double *h_c0, const ttmpc_result *res);

@@ -191,6 +191,49 @@ def test_device_resident_api_matches_host_api(cfg, solver):
     assert np.array_equal(dev.exit_status.cpu().numpy(), host.exit_status)
 
 
+@pytest.mark.parametrize("code", ["small", "unrolled"])
+def test_both_builds_of_the_solve_kernel_match_the_oracle(cfg, solver, monkeypatch, code):
+    """The library holds the solve kernel twice (hot loops unrolled / rolled) and picks by batch
+    size; forced either way the results are the oracle's, bit for bit."""
+    monkeypatch.setenv("TTMPC_CODE", code)
+    p = t.scenes.make_scenes(160, cfg, seed=91, n_static=4, n_dynamic=3, blocking_fraction=0.2)
+    sol = solver.run(p)
+    ref = O.solve_batch(cfg, p, threads=8, warp=True)
+    assert_parity(sol, ref, 160)
+
+
+def test_batches_in_flight_on_several_streams_and_host_threads(cfg, solver):
+    """Consecutive batches may overlap on the GPU (one scene queue per stream / per host call):
+    every batch still gets exactly the results of a solve that had the GPU to itself."""
+    import torch
+    ps = [t.scenes.make_scenes(2500, cfg, seed=70 + j, n_static=4, n_dynamic=j % 2, blocking_fraction=0.1)
+          for j in range(3)]
+    alone = [solver.run(p) for p in ps]
+    # host path, three calls in flight, twice over (slots are reused)
+    many = solver.run_many(ps + ps, depth=3)
+    for j, sol in enumerate(many):
+        a = alone[j % 3]
+        assert np.array_equal(sol.solution, a.solution) and np.array_equal(sol.cost, a.cost)
+        assert np.array_equal(sol.exit_status, a.exit_status)
+        assert np.array_equal(sol.lagrange_multipliers, a.lagrange_multipliers)
+        assert np.array_equal(sol.pred_states, a.pred_states)
+    # device path, one stream per batch
+    dps = [torch.from_numpy(p).cuda() for p in ps]
+    bufs = [solver.alloc_device(len(p)) for p in ps]
+    streams = [torch.cuda.Stream() for _ in ps]
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for j in range(3):
+            with torch.cuda.stream(streams[j]):
+                solver.run_device(dps[j], bufs[j])
+    torch.cuda.synchronize()
+    for j in range(3):
+        assert np.array_equal(bufs[j]["u"].cpu().numpy(), alone[j].solution)
+        assert np.array_equal(bufs[j]["cost"].cpu().numpy(), alone[j].cost)
+        assert np.array_equal(bufs[j]["exit_status"].cpu().numpy(), alone[j].exit_status)
+        assert np.array_equal(bufs[j]["inner"].cpu().numpy(), alone[j].num_inner_iterations)
+
+
 # ------------------------------------------------------------------ reference-facing objects
 def test_solver_object_mirrors_open_binding(cfg):
     """Solver.run(p, initial_guess) like trajectory_generator.py:284: fields, statefulness

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -94,6 +95,10 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
       return fail(TTMPC_ERR_UNSUPPORTED, "configuration does not fit in shared memory: " +
                   std::to_string(g->smem_per_warp) + " bytes of tables per scene, 227 KB per SM");
     int wpb = 4;
+    if (const char *e = std::getenv("TTMPC_WARPS_PER_BLOCK")) {  // tuning: scenes per CTA (1..4)
+      const int v = std::atoi(e);
+      if (v >= 1 && v <= 4) wpb = v;
+    }
     while (wpb > 1 && (size_t)g->smem_per_warp * wpb > cap) wpb--;
     g->warps_per_block = wpb;
   }
@@ -107,22 +112,38 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
 }
 
 // ---------------------------------------------------------------- per-device workspace
-struct Workspace {
-  int device = -1;
-  int sm_count = 0;
+// A Slot is everything ONE in-flight solve owns: the scene queue counter, the running average
+// behind the early helpers, the dispatch order, the per-warp dynamic-obstacle tables and (host
+// path) the streams, the `ready` counter and the staging buffers.  Solves issued on different
+// CUDA streams (device path) or from different host threads (host path) get different slots, so
+// consecutive batches can overlap on the GPU: the CTAs of batch k+1 become resident as the CTAs
+// of batch k drain, and the tail of one batch (a handful of long scenes) is filled with the
+// bulk of the next.  Solves on one stream are ordered by the stream and share a slot.
+struct Slot {
+  bool keyed = false;              // device path: bound to `key`
+  cudaStream_t key = nullptr;
+  bool host = false, host_busy = false;  // host path: taken by one ttmpc_solve_batch_host call at a time
   double *dyn_scratch = nullptr; size_t dyn_bytes = 0;
   int *work_counter = nullptr;
-  int *ready = nullptr;           // device counter of scenes already copied (host path)
+  unsigned long long *run_stats = nullptr;  // [0] evaluations, [1] finished scenes of the running launch
+  int *ready = nullptr;           // device counter of scenes already copied (host path) + time-out flag
   int *h_ready = nullptr;         // pinned: one value per chunk
   cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
   cudaEvent_t ev_inputs = nullptr;
-  unsigned long long *stats = nullptr;
   int *order = nullptr; size_t order_ints = 0;  // dispatch order + ranking scratch
   // device staging for the host API
   void *dbuf = nullptr; size_t dbytes = 0;
   void *hbuf = nullptr; size_t hbytes = 0;
 };
+constexpr int MAX_STREAM_SLOTS = 16, MAX_HOST_SLOTS = 8;
+struct Workspace {
+  int device = -1;
+  int sm_count = 0;
+  unsigned long long *stats = nullptr;  // 24 x u64, shared by every slot (atomics)
+  std::vector<Slot *> slots;
+};
 static std::mutex g_mu;
+static std::condition_variable g_cv;
 static std::vector<Workspace> g_ws;
 
 static int get_ws(Workspace **out) {
@@ -133,20 +154,76 @@ static int get_ws(Workspace **out) {
   Workspace w;
   w.device = dev;
   CUDA_TRY(cudaDeviceGetAttribute(&w.sm_count, cudaDevAttrMultiProcessorCount, dev));
-  CUDA_TRY(cudaMalloc(&w.work_counter, 64));
   CUDA_TRY(cudaMalloc(&w.stats, 192));
   CUDA_TRY(cudaMemset(w.stats, 0, 192));
-  CUDA_TRY(cudaMalloc(&w.ready, 64));
-  CUDA_TRY(cudaHostAlloc(&w.h_ready, sizeof(int) * 4096, cudaHostAllocDefault));
-  CUDA_TRY(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&w.exec_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&w.ev_inputs, cudaEventDisableTiming));
   g_ws.reserve(16);
   g_ws.push_back(w);
   *out = &g_ws.back();
   return TTMPC_OK;
 }
-static int ensure_dyn(Workspace *w, size_t bytes) {
+static int new_slot(Workspace *w, Slot **out) {
+  Slot *s = new Slot();
+  CUDA_TRY(cudaMalloc(&s->work_counter, 64));
+  CUDA_TRY(cudaMalloc(&s->run_stats, 64));
+  CUDA_TRY(cudaMemset(s->run_stats, 0, 64));
+  CUDA_TRY(cudaMalloc(&s->ready, 64));
+  w->slots.push_back(s);
+  *out = s;
+  return TTMPC_OK;
+}
+// device path: the slot of this stream (g_mu held)
+static int slot_for_stream(Workspace *w, cudaStream_t st, Slot **out) {
+  int keyed = 0;
+  for (Slot *s : w->slots) {
+    if (s->keyed && s->key == st) { *out = s; return TTMPC_OK; }
+    keyed += s->keyed ? 1 : 0;
+  }
+  if (keyed >= MAX_STREAM_SLOTS)
+    return fail(TTMPC_ERR_UNSUPPORTED, "more than 16 distinct CUDA streams have issued solves on this device");
+  int rc = new_slot(w, out);
+  if (rc) return rc;
+  (*out)->keyed = true; (*out)->key = st;
+  return TTMPC_OK;
+}
+// host path: a free host slot (waits when MAX_HOST_SLOTS calls are already in flight)
+static int acquire_host_slot(Workspace **wout, Slot **out) {
+  std::unique_lock<std::mutex> lk(g_mu);
+  Workspace *w;
+  int rc = get_ws(&w);
+  if (rc) return rc;
+  *wout = w;
+  while (true) {
+    int hosts = 0;
+    for (Slot *s : w->slots) {
+      if (!s->host) continue;
+      hosts++;
+      if (!s->host_busy) { s->host_busy = true; *out = s; return TTMPC_OK; }
+    }
+    if (hosts < MAX_HOST_SLOTS) break;
+    g_cv.wait(lk);
+  }
+  Slot *s;
+  rc = new_slot(w, &s);
+  if (rc) return rc;
+  s->host = true; s->host_busy = true;
+  CUDA_TRY(cudaHostAlloc(&s->h_ready, sizeof(int) * 4096, cudaHostAllocDefault));
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->exec_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&s->ev_inputs, cudaEventDisableTiming));
+  *out = s;
+  return TTMPC_OK;
+}
+namespace {
+struct HostSlotLease {  // returns the slot when the host call ends, whatever the exit path
+  Slot *s = nullptr;
+  ~HostSlotLease() {
+    if (!s) return;
+    { std::lock_guard<std::mutex> lk(g_mu); s->host_busy = false; }
+    g_cv.notify_one();
+  }
+};
+}  // namespace
+static int ensure_dyn(Slot *w, size_t bytes) {
   if (bytes <= w->dyn_bytes) return TTMPC_OK;
   if (w->dyn_scratch) CUDA_TRY(cudaFree(w->dyn_scratch));
   w->dyn_scratch = nullptr; w->dyn_bytes = 0;
@@ -154,7 +231,7 @@ static int ensure_dyn(Workspace *w, size_t bytes) {
   w->dyn_bytes = bytes;
   return TTMPC_OK;
 }
-static int ensure_order(Workspace *w, size_t ints) {
+static int ensure_order(Slot *w, size_t ints) {
   if (ints <= w->order_ints) return TTMPC_OK;
   if (w->order) CUDA_TRY(cudaFree(w->order));
   w->order = nullptr; w->order_ints = 0;
@@ -162,7 +239,7 @@ static int ensure_order(Workspace *w, size_t ints) {
   w->order_ints = ints;
   return TTMPC_OK;
 }
-static int ensure_staging(Workspace *w, size_t bytes) {
+static int ensure_staging(Slot *w, size_t bytes) {
   if (bytes > w->dbytes) {
     if (w->dbuf) CUDA_TRY(cudaFree(w->dbuf));
     w->dbuf = nullptr; w->dbytes = 0;
@@ -194,7 +271,7 @@ static int grid_for(Workspace *w, const DevCfg &g, int n_scenes, int *grid) {
 
 static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double *d_p, int use_u0,
                              int use_y0, const double *d_c0, const ttmpc_result *res,
-                             cudaStream_t st, const int *d_ready);
+                             cudaStream_t st, Slot *host_slot, bool gated);
 
 // warps per CTA of the split kernel: as many scene regions as fit the 227 KB of one SM (<= 12)
 static int split_warps(const DevCfg &g) {
@@ -209,12 +286,12 @@ static bool use_split(const DevCfg &g) {
 extern "C" int ttmpc_solve_batch_device(const ttmpc_config *cfg, int n_scenes, const double *d_p,
                                         int use_u0, int use_y0, const double *d_c0,
                                         const ttmpc_result *res, void *stream) {
-  return solve_device_impl(cfg, n_scenes, d_p, use_u0, use_y0, d_c0, res, (cudaStream_t)stream, nullptr);
+  return solve_device_impl(cfg, n_scenes, d_p, use_u0, use_y0, d_c0, res, (cudaStream_t)stream, nullptr, false);
 }
 
 static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double *d_p, int use_u0,
                              int use_y0, const double *d_c0, const ttmpc_result *res,
-                             cudaStream_t st, const int *d_ready) {
+                             cudaStream_t st, Slot *host_slot, bool gated) {
   DevCfg g;
   int rc = make_devcfg(cfg, &g);
   if (rc) return rc;
@@ -225,6 +302,11 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   Workspace *w;
   rc = get_ws(&w);
   if (rc) return rc;
+  // host path: the caller's slot (streamed inputs gated by its `ready` counter); device path:
+  // the slot of the stream
+  Slot *sl = host_slot;
+  if (!sl) { rc = slot_for_stream(w, st, &sl); if (rc) return rc; }
+  const int *d_ready = (host_slot && gated) ? host_slot->ready : nullptr;
   int grid;
   rc = grid_for(w, g, n_scenes, &grid);
   if (rc) return rc;
@@ -236,21 +318,21 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
     const long long want = ((long long)n_scenes + gs.warps_per_block - 1) / gs.warps_per_block;
     clusters = (int)std::min<long long>(std::max(1, w->sm_count / 2), want);
   }
-  rc = ensure_dyn(w, (table ? table : 8) * std::max((size_t)grid * g.warps_per_block,
-                                                    (size_t)clusters * gs.warps_per_block));
+  rc = ensure_dyn(sl, (table ? table : 8) * std::max((size_t)grid * g.warps_per_block,
+                                                     (size_t)clusters * gs.warps_per_block));
   if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(w->work_counter, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(sl->work_counter, 0, sizeof(int), st));
   const char *nh = std::getenv("TTMPC_NO_HELPERS");
   SolveArgs A;
   A.eprof = w->stats + 8;  // stats block is 24 x u64: [0..7] counters, [8..17] eval sections
   A.helpers = (nh && nh[0] == '1') ? 0 : 1;  // TTMPC_NO_HELPERS=1 disables the tail helpers
-  A.ready = d_ready; A.timeout_flag = d_ready ? w->ready + 1 : nullptr;
+  A.ready = d_ready; A.timeout_flag = d_ready ? sl->ready + 1 : nullptr;
   A.p = d_p; A.c0 = d_c0; A.u = res->u; A.y = res->y; A.cost = res->cost;
   A.last_fpr = res->last_fpr; A.f1_infeas = res->f1_infeas; A.f2_norm = res->f2_norm;
   A.penalty = res->penalty; A.exit_status = res->exit_status; A.outer_iters = res->outer_iters;
   A.inner_iters = res->inner_iters; A.pred_states = res->pred_states; A.evals = res->evals;
-  A.dyn_scratch = w->dyn_scratch; A.work_counter = w->work_counter; A.stats = w->stats;
-  A.run_stats = w->stats + 18;  // stats block: [18] evaluations, [19] count of finished scenes
+  A.dyn_scratch = sl->dyn_scratch; A.work_counter = sl->work_counter; A.stats = w->stats;
+  A.run_stats = sl->run_stats;  // [0] evaluations, [1] count of finished scenes of this launch
   { const char *ne = std::getenv("TTMPC_NO_EARLY_HELP"); if (ne && ne[0] == '1') A.run_stats = nullptr; }
   // the running average behind the early-helper threshold is per launch (workloads differ by 30x)
   if (A.run_stats) CUDA_TRY(cudaMemsetAsync(A.run_stats, 0, 2 * sizeof(unsigned long long), st));
@@ -263,13 +345,22 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
     const long long resident = clusters > 0 ? (long long)clusters * gs.warps_per_block
                                             : (long long)grid * g.warps_per_block;
     if (!d_ready && n_scenes > resident && !(no && no[0] == '1')) {
-      rc = ensure_order(w, 2 * (size_t)n_scenes + 64);
+      rc = ensure_order(sl, 2 * (size_t)n_scenes + 64);
       if (rc) return rc;
-      CUDA_TRY(launch_rank_scenes(g, d_p, n_scenes, w->order + n_scenes, w->order, st));
-      A.order = w->order;
+      CUDA_TRY(launch_rank_scenes(g, d_p, n_scenes, sl->order + n_scenes, sl->order, st));
+      A.order = sl->order;
     }
   }
+  // two builds of the same kernel, bit-identical results: unrolled hot loops when every scene has a
+  // warp from the start (latency-bound), rolled loops when the batch queues behind the resident
+  // warps (bound by the instruction cache with 12 warps per SM).  TTMPC_CODE=small|unrolled forces one.
+  bool small_code = n_scenes > (long long)grid * g.warps_per_block;
+  if (const char *e = std::getenv("TTMPC_CODE")) {
+    if (e[0] == 's') small_code = true;
+    else if (e[0] == 'u') small_code = false;
+  }
   if (clusters > 0) CUDA_TRY(launch_solve_split(gs, A, clusters, st));
+  else if (small_code) CUDA_TRY(launch_solve_small(g, A, grid, st));
   else CUDA_TRY(launch_solve(g, A, grid, st));
   return TTMPC_OK;
 }
@@ -405,14 +496,15 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   const size_t nn = (size_t)n, nu = 2 * (size_t)g.N;
   size_t total = 4096 + 256 * 16 + sizeof(double) * (nn * g.np + nn + 2 * nn * nu + 5 * nn + nn * g.N * 3) +
                  sizeof(int) * 3 * nn + sizeof(long long) * 4 * nn;
-  Workspace *w;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    rc = get_ws(&w);
-    if (rc) return rc;
-    rc = ensure_staging(w, total);
-    if (rc) return rc;
-  }
+  // every call owns a slot (staging buffers, two streams, `ready` counter) until it returns:
+  // calls from several host threads overlap on the GPU
+  Workspace *ws;
+  Slot *w = nullptr;
+  rc = acquire_host_slot(&ws, &w);
+  HostSlotLease lease{w};
+  if (rc) return rc;
+  rc = ensure_staging(w, total);
+  if (rc) return rc;
   Carver cv{(char *)w->dbuf, (char *)w->hbuf};
   double *dp, *hp, *dc0, *hc0, *du, *hu, *dy, *hy, *dcost, *hcost, *dfpr, *hfpr, *df1, *hf1, *df2,
       *hf2, *dpen, *hpen, *dps, *hps;
@@ -463,7 +555,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING");
   const bool stream_in = !(ns && ns[0] == '1') && !(lb && lb[0] == '1');
   if (stream_in) {
-    rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w->ready);
+    rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w, true);
     if (rc) return rc;
   }
   {
@@ -521,7 +613,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
     CUDA_TRY(cudaStreamSynchronize(cs));
     if (use_u0) CUDA_TRY(cudaMemcpyAsync(du, hu, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
     if (use_y0 && res->y) CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
-    rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, nullptr);
+    rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w, false);
     if (rc) return rc;
   }
   // one contiguous D2H of everything after the inputs
@@ -561,11 +653,14 @@ extern "C" int ttmpc_eval_batch_device(const ttmpc_config *cfg, int n, const dou
   rc = grid_for(w, g, n, &grid);
   if (rc) return rc;
   const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
-  rc = ensure_dyn(w, (table ? table : 8) * (size_t)grid * g.warps_per_block);
+  Slot *sl;
+  rc = slot_for_stream(w, (cudaStream_t)stream, &sl);
+  if (rc) return rc;
+  rc = ensure_dyn(sl, (table ? table : 8) * (size_t)grid * g.warps_per_block);
   if (rc) return rc;
   EvalArgs A;
   A.p = d_p; A.u = d_u; A.c = d_c; A.y = d_y; A.f = d_f; A.F1 = d_F1; A.F2 = d_F2; A.psi = d_psi;
-  A.grad = d_grad; A.dyn_scratch = w->dyn_scratch; A.n_scenes = n;
+  A.grad = d_grad; A.dyn_scratch = sl->dyn_scratch; A.n_scenes = n;
   CUDA_TRY(launch_eval(g, A, grid, (cudaStream_t)stream));
   return TTMPC_OK;
 }

@@ -116,6 +116,22 @@ class BatchSolver:
                              out["fpr"], out["f1"], out["f2"], out["pen"], y, out["pred"],
                              out["evals"], ms)
 
+    def run_many(self, batches, depth: int = 3, **kw) -> List[BatchSolution]:
+        """Solve several host batches with up to ``depth`` of them in flight.
+
+        Each batch is one ``run`` call (same arguments, same results) issued from its own host
+        thread; the library gives every in-flight call its own staging buffers, streams and
+        scene queue, so the next batch's copies and bulk overlap the tail of the previous one
+        (a 4096-scene batch ends with a handful of long scenes that keep 1 % of the GPU busy).
+        Results are returned in the order of ``batches``.
+        """
+        from concurrent.futures import ThreadPoolExecutor
+        batches = list(batches)
+        if depth <= 1 or len(batches) <= 1:
+            return [self.run(p, **kw) for p in batches]
+        with ThreadPoolExecutor(max_workers=min(depth, 8)) as ex:
+            return list(ex.map(lambda p: self.run(p, **kw), batches))
+
     # -------------------------------------------------------------- device tensors
     def alloc_device(self, n: int, device="cuda", want_pred_states: bool = True):
         """Allocate the output tensors of ``run_device`` once (reused across steps)."""
@@ -134,6 +150,9 @@ class BatchSolver:
     def run_device(self, p, bufs: dict, use_u0: bool = False, use_y0: bool = False, c0=None,
                    stream=None) -> BatchSolution:
         """p: torch.float64 CUDA tensor [n, np].  Asynchronous on the current torch stream.
+
+        Solves issued on different streams (with different ``bufs``) overlap on the GPU: each
+        stream has its own scene queue and scratch tables inside the library.
 
         With use_u0 / use_y0 the initial guess / multipliers are read from
         bufs['u'] / bufs['y'], which are overwritten with the results.
