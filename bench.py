@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--workload", default="static4096")
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (1 = one at a time)")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight (1 = one at a time)")
     ap.add_argument("--batches", type=int, default=4, help="distinct input batches the steps rotate through")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

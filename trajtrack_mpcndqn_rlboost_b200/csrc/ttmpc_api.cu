@@ -88,18 +88,26 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   g->np = g->off_qdyn + N;
   g->smem_per_warp = smem_bytes_per_warp(N, g->Nother, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
   {
-    // 4 scenes per CTA when they fit the 227 KB a CTA can opt in to (3 CTAs per SM for the default
-    // shapes), fewer for large configurations; one scene must fit
+    // 2 scenes per CTA (6 CTAs per SM for the default shapes: 12 resident scenes per SM, each owner
+    // has one potential helper).  Small CTAs release their SM share as soon as both scenes are done,
+    // which is what lets the next batch in (batches in flight: +4 % over 4 scenes per CTA, same
+    // time for a batch alone).  Large configurations: one scene per CTA if two do not fit.
     const size_t cap = 232448 - 256;
     if ((size_t)g->smem_per_warp > cap)
       return fail(TTMPC_ERR_UNSUPPORTED, "configuration does not fit in shared memory: " +
                   std::to_string(g->smem_per_warp) + " bytes of tables per scene, 227 KB per SM");
-    int wpb = 4;
+    // larger tables: the CTA size (2, 3, 4, else 1 scene) that keeps the most scenes resident per SM
+    int wpb = 1, best = 0;
+    for (int cand : {2, 3, 4, 1}) {
+      const size_t per_cta = (size_t)g->smem_per_warp * cand + 96 + 1024;  // + CtaHelp + the 1 KB the driver reserves per CTA
+      if ((size_t)g->smem_per_warp * cand > cap) continue;
+      const int ctas = (int)std::min<size_t>(233472 / per_cta, (size_t)(12 / cand));
+      if (ctas * cand > best) { best = ctas * cand; wpb = cand; }
+    }
     if (const char *e = std::getenv("TTMPC_WARPS_PER_BLOCK")) {  // tuning: scenes per CTA (1..4)
       const int v = std::atoi(e);
-      if (v >= 1 && v <= 4) wpb = v;
+      if (v >= 1 && v <= 4 && (size_t)g->smem_per_warp * v <= cap) wpb = v;
     }
-    while (wpb > 1 && (size_t)g->smem_per_warp * wpb > cap) wpb--;
     g->warps_per_block = wpb;
   }
   g->ts = c->ts; g->inv_ts = 1.0 / c->ts; g->h6 = c->ts / 6.0; g->veh_d2 = c->vehicle_width * c->vehicle_width; g->margin = c->social_margin;

@@ -116,7 +116,7 @@ class BatchSolver:
                              out["fpr"], out["f1"], out["f2"], out["pen"], y, out["pred"],
                              out["evals"], ms)
 
-    def run_many(self, batches, depth: int = 3, **kw) -> List[BatchSolution]:
+    def run_many(self, batches, depth: int = 6, **kw) -> List[BatchSolution]:
         """Solve several host batches with up to ``depth`` of them in flight.
 
         Each batch is one ``run`` call (same arguments, same results) issued from its own host
