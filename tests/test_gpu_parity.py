@@ -189,6 +189,12 @@ def test_device_resident_api_matches_host_api(cfg, solver):
     assert np.array_equal(dev.solution.cpu().numpy(), host.solution)
     assert np.array_equal(dev.cost.cpu().numpy(), host.cost)
     assert np.array_equal(dev.exit_status.cpu().numpy(), host.exit_status)
+    # parameters in page-locked host memory are copied from directly (no staging memcpy): same results
+    pp = t.pinned_empty(p.shape)
+    pp[...] = p
+    pin = solver.run(pp)
+    assert np.array_equal(pin.solution, host.solution) and np.array_equal(pin.cost, host.cost)
+    assert np.array_equal(pin.exit_status, host.exit_status)
 
 
 @pytest.mark.parametrize("code", ["small", "unrolled"])

@@ -194,14 +194,16 @@ static int slot_for_stream(Workspace *w, cudaStream_t st, Slot **out) {
   return TTMPC_OK;
 }
 // host path: a free host slot (waits when MAX_HOST_SLOTS calls are already in flight)
-static int acquire_host_slot(Workspace **wout, Slot **out) {
+static int acquire_host_slot(Workspace **wout, Slot **out, int *busy_calls) {
   std::unique_lock<std::mutex> lk(g_mu);
   Workspace *w;
   int rc = get_ws(&w);
   if (rc) return rc;
   *wout = w;
   while (true) {
-    int hosts = 0;
+    int hosts = 0, busy = 1;
+    for (Slot *s : w->slots) busy += (s->host && s->host_busy) ? 1 : 0;
+    *busy_calls = busy;
     for (Slot *s : w->slots) {
       if (!s->host) continue;
       hosts++;
@@ -508,7 +510,8 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   // calls from several host threads overlap on the GPU
   Workspace *ws;
   Slot *w = nullptr;
-  rc = acquire_host_slot(&ws, &w);
+  int busy_calls = 1;
+  rc = acquire_host_slot(&ws, &w, &busy_calls);
   HostSlotLease lease{w};
   if (rc) return rc;
   rc = ensure_staging(w, total);
@@ -566,17 +569,31 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
     rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w, true);
     if (rc) return rc;
   }
+  // Pinned (page-locked) caller memory is copied from directly; pageable memory goes through the
+  // slot's pinned staging buffer first (a host memcpy, ~10 GB/s per thread).
+  bool pinned_in = false;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h_p) == cudaSuccess) pinned_in = at.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    const char *np_ = std::getenv("TTMPC_NO_PINNED_INPUT");
+    if (np_ && np_[0] == '1') pinned_in = false;
+  }
   {
     int chunk = 256;
     while ((n + chunk - 1) / chunk > 4096) chunk *= 2;
     const int n_chunks = (n + chunk - 1) / chunk;
-    // The copy into pinned staging is host-memory bound (~10 GB/s per thread) and the kernel
-    // cannot run ahead of it: a few worker threads stage the chunks (chunk i by thread i mod T),
-    // this thread issues the H2D copies in order as the chunks become ready.
+    // The copy into pinned staging is host-memory bound and the kernel cannot run ahead of it: a
+    // few worker threads stage the chunks (chunk i by thread i mod T), this thread issues the H2D
+    // copies in order as the chunks become ready.  The team shrinks when several calls are in
+    // flight (TTMPC_HOST_THREADS = thread budget of this process, default half the cores).
     const unsigned hw = std::thread::hardware_concurrency();
-    const int T = std::max(1, std::min({8, (int)(hw ? hw / 2 : 1), n_chunks}));
+    int budget = (int)(hw ? hw / 2 : 1);
+    if (const char *e = std::getenv("TTMPC_HOST_THREADS")) { const int v = std::atoi(e); if (v >= 1) budget = v; }
+    const int T = pinned_in ? 1 : std::max(1, std::min({8, budget / std::max(1, busy_calls), n_chunks}));
+    const double *src = pinned_in ? h_p : hp;
     std::vector<std::atomic<int>> staged(n_chunks);
-    for (auto &f : staged) f.store(0, std::memory_order_relaxed);
+    for (auto &f : staged) f.store(pinned_in ? 1 : 0, std::memory_order_relaxed);
     auto stage = [&](int t) {
       for (int ci = t; ci < n_chunks; ci += T) {
         const int s0 = ci * chunk, s1 = s0 + chunk < n ? s0 + chunk : n;
@@ -604,7 +621,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
       const int s0 = ci * chunk, s1 = s0 + chunk < n ? s0 + chunk : n;
       const size_t off = (size_t)s0 * g.np, cnt = (size_t)(s1 - s0) * g.np;
       if (rc_copy == TTMPC_OK &&
-          (cudaMemcpyAsync(dp + off, hp + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+          (cudaMemcpyAsync(dp + off, src + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
            (w->h_ready[ci] = s1,
             cudaMemcpyAsync(w->ready, w->h_ready + ci, sizeof(int), cudaMemcpyHostToDevice, cs) != cudaSuccess)))
         rc_copy = TTMPC_ERR_CUDA;

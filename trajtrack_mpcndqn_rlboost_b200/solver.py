@@ -66,6 +66,16 @@ class BatchSolution:
         return [EXIT_STATUS_NAMES[c] for c in codes]
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """A numpy array in page-locked host memory (a view of a pinned torch tensor).  Parameter blocks
+    built in such an array are copied to the GPU straight from it; ordinary (pageable) arrays
+    are staged through the library's own pinned buffer first, which costs a host memcpy."""
+    import torch
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+           np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
+    return torch.empty(tuple(np.atleast_1d(shape)), dtype=tdt).pin_memory().numpy()
+
+
 def _ptr(a) -> Optional[int]:
     return None if a is None else a.ctypes.data
 
