@@ -88,8 +88,8 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   g->np = g->off_qdyn + N;
   g->smem_per_warp = smem_bytes_per_warp(N, g->Nother, g->Nstc, g->nstcobs, g->Ndyn, g->mem);
   {
-    // 2 scenes per CTA (6 CTAs per SM for the default shapes: 12 resident scenes per SM, each owner
-    // has one potential helper).  Small CTAs release their SM share as soon as both scenes are done,
+    // 2 scenes per CTA (4 CTAs per SM for the default shapes: 8 resident scenes per SM at 255
+    // registers per thread, each owner has one potential helper).  Small CTAs release their SM share as soon as both scenes are done,
     // which is what lets the next batch in (batches in flight: +4 % over 4 scenes per CTA, same
     // time for a batch alone).  Large configurations: one scene per CTA if two do not fit.
     const size_t cap = 232448 - 256;
@@ -101,7 +101,7 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
     for (int cand : {2, 3, 4, 1}) {
       const size_t per_cta = (size_t)g->smem_per_warp * cand + 96 + 1024;  // + CtaHelp + the 1 KB the driver reserves per CTA
       if ((size_t)g->smem_per_warp * cand > cap) continue;
-      const int ctas = (int)std::min<size_t>(233472 / per_cta, (size_t)(12 / cand));
+      const int ctas = (int)std::min<size_t>(233472 / per_cta, (size_t)(8 / cand));
       if (ctas * cand > best) { best = ctas * cand; wpb = cand; }
     }
     if (const char *e = std::getenv("TTMPC_WARPS_PER_BLOCK")) {  // tuning: scenes per CTA (1..4)
