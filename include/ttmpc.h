@@ -139,8 +139,8 @@ typedef struct ttmpc_result {
  *               keeps them between run() calls; the host mirror does that.)
  *   d_c0      : optional per-scene initial penalty (NULL -> cfg value).
  * Batches in flight: solves issued on the SAME stream run one after the other;
- * solves issued on DIFFERENT streams (at most 16 per device, each with its own
- * result buffers) may overlap -- every stream has its own scene queue and scratch
+ * solves issued on DIFFERENT streams (each with its own result buffers; 16 stream
+ * bindings per device, a 17th stream drains the device once and rebinds) may overlap -- every stream has its own scene queue and scratch
  * tables inside the library, and the CTAs of the next batch become resident as
  * the CTAs of the running one drain.  Results do not depend on what else runs.
  * ------------------------------------------------------------------------ */

@@ -240,6 +240,23 @@ def test_batches_in_flight_on_several_streams_and_host_threads(cfg, solver):
         assert np.array_equal(bufs[j]["inner"].cpu().numpy(), alone[j].num_inner_iterations)
 
 
+def test_more_streams_than_stream_bindings(cfg, solver):
+    """20 streams on a library that keeps 16 stream bindings: the 17th drains and rebinds."""
+    import torch
+    p = t.scenes.make_scenes(64, cfg, seed=5, n_static=3, n_dynamic=1)
+    alone = solver.run(p)
+    dp = torch.from_numpy(p).cuda()
+    streams = [torch.cuda.Stream() for _ in range(20)]
+    bufs = [solver.alloc_device(64) for _ in streams]
+    torch.cuda.synchronize()
+    for st, b in zip(streams, bufs):
+        with torch.cuda.stream(st):
+            solver.run_device(dp, b)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert np.array_equal(b["u"].cpu().numpy(), alone.solution)
+
+
 # ------------------------------------------------------------------ reference-facing objects
 def test_solver_object_mirrors_open_binding(cfg):
     """Solver.run(p, initial_guess) like trajectory_generator.py:284: fields, statefulness

@@ -55,7 +55,8 @@ def main():
     out = dict(workload=f"fleet{n}", robots=n, steps=steps, step_ms_p50=q(t_step, 0.5), step_ms_p90=q(t_step, 0.9),
                robot_steps_per_s=n / (q(t_step, 0.5) * 1e-3), pack_ms_p50=q(t_pack, 0.5), advance_ms_p50=q(t_adv, 0.5),
                pack_GBps=pack_bytes / (q(t_pack, 0.5) * 1e-3) / 1e9, hbm_peak_GBps=peaks.get("hbm_gbs"),
-               mean_inner_iters=float(np.mean(iters)), running_last=running[-1])
+               mean_inner_iters=float(np.mean(iters)), running_last=running[-1],
+               step_ms=[round(x, 1) for x in t_step], inner_iters=[round(x, 1) for x in iters])
     # CPU: the same step with the oracle (reference operation order), bounded sample
     ns = min(n, 256)
     tuning, base = work_mode(mc, "work")

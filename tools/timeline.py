@@ -21,7 +21,7 @@ print("per-scene ms: mean %.3f median %.3f p90 %.3f p99 %.3f max %.3f sum %.1f" 
 print("last finish ms %.3f; start of the slowest %.3f; evals of slowest %d; us/eval (slowest) %.2f; us/eval overall %.2f" % ((start + dur).max(), start[dur.argmax()], n_ev[dur.argmax()], 1e3 * dur.max() / n_ev[dur.argmax()], 1e3 * dur.sum() / n_ev.sum()))
 order = np.argsort(-dur)[:8]
 print("slowest:", [(int(i), round(float(dur[i]), 2), int(n_ev[i]), round(float(start[i]), 2)) for i in order])
-slots = s.launch_info(len(p))["grid"] * 4
+li = s.launch_info(len(p)); slots = li["grid"] * li["block"] // 32
 print("warp slots", slots, "ideal balanced ms", dur.sum() / slots)
 fin = start + dur
 late = np.argsort(-fin)[:8]

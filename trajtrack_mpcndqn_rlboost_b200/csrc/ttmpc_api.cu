@@ -179,19 +179,33 @@ static int new_slot(Workspace *w, Slot **out) {
   *out = s;
   return TTMPC_OK;
 }
-// device path: the slot of this stream (g_mu held)
+// device path: the slot of this stream (g_mu held).  Bindings are kept while they fit; when a 17th
+// stream shows up the device is drained once and every binding is dropped (streams come and go --
+// a destroyed stream cannot be told from an idle one -- and an unbound slot keeps its buffers).
 static int slot_for_stream(Workspace *w, cudaStream_t st, Slot **out) {
-  int keyed = 0;
-  for (Slot *s : w->slots) {
-    if (s->keyed && s->key == st) { *out = s; return TTMPC_OK; }
-    keyed += s->keyed ? 1 : 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int device_slots = 0;
+    Slot *free_slot = nullptr;
+    for (Slot *s : w->slots) {
+      if (s->host) continue;
+      device_slots++;
+      if (s->keyed && s->key == st) { *out = s; return TTMPC_OK; }
+      if (!s->keyed && !free_slot) free_slot = s;
+    }
+    if (!free_slot && device_slots < MAX_STREAM_SLOTS) {
+      int rc = new_slot(w, &free_slot);
+      if (rc) return rc;
+    }
+    if (free_slot) {
+      free_slot->keyed = true; free_slot->key = st;
+      *out = free_slot;
+      return TTMPC_OK;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (Slot *s : w->slots)
+      if (!s->host) s->keyed = false;
   }
-  if (keyed >= MAX_STREAM_SLOTS)
-    return fail(TTMPC_ERR_UNSUPPORTED, "more than 16 distinct CUDA streams have issued solves on this device");
-  int rc = new_slot(w, out);
-  if (rc) return rc;
-  (*out)->keyed = true; (*out)->key = st;
-  return TTMPC_OK;
+  return fail(TTMPC_ERR_CUDA, "no scene-queue slot for this stream");
 }
 // host path: a free host slot (waits when MAX_HOST_SLOTS calls are already in flight)
 static int acquire_host_slot(Workspace **wout, Slot **out, int *busy_calls) {
