@@ -3,6 +3,12 @@
 
 One "step" = one pass of the hot path over one batch of synthetic scenes:
 solve every scene of the workload once (PANOC + ALM to the reference's tolerances).
+The K timed steps rotate through 4 distinct input batches (more bytes than L2 holds) with up
+to --depth of them in flight, each on its own stream: `value` is
+scenes / time of all K steps, every step complete inside the timed region.  `sequential`
+repeats the steps one batch at a time (the latency of one batch).  `e2e` is the same through
+BatchSolver.run_many with pinned host buffers (H2D of the parameters and D2H of every result
+field inside the timed region).
 
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -173,6 +179,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the solver has no CPU path")
+    # host threads this rank may use for staging pageable inputs: its share of half the cores
+    os.environ.setdefault("TTMPC_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // (2 * max(1, world)))))
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -314,9 +322,10 @@ def main():
     achieved = flops / (local_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch on this
-                # workload, ncu --set full capture profiles/r1_f_solve_kernel_final.txt
-                "traffic": 144.6e6 if args.workload == "static4096" else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel_small launch on this
+                # workload, ncu --set full capture profiles/r1_h_solve_kernel_255_registers.txt
+                # (algorithmic: 87.1 MB of parameters in + 4.9 MB of results out)
+                "traffic": 99.4e6 if args.workload == "static4096" else None,
                 "peak_source": "measured live: DFMA probe kernel (ttmpc_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "hbm_GBps_algorithmic": (p_host.nbytes + d2h) / (local_ms * 1e-3) / 1e9,

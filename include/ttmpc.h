@@ -110,6 +110,11 @@ int ttmpc_num_penalty(const ttmpc_config *cfg); /* n2 = Ndynobs */
 const char *ttmpc_last_error(void);
 const char *ttmpc_exit_status_name(int code);
 int ttmpc_version(void);
+/* The CUDA device of the CALLING THREAD (cudaSetDevice / cudaGetDevice): every entry point works on
+ * the calling thread's current device, so a host thread that serves GPU k calls ttmpc_set_device(k)
+ * once before its first solve (new threads start on device 0).                                  */
+int ttmpc_set_device(int device);
+int ttmpc_get_device(int *device);
 
 /* Per-scene outputs of a batched solve.  Any pointer may be NULL (skipped)
  * except u.  Mirrors the fields of OpEn's python OptimizerSolution that the

@@ -91,6 +91,8 @@ SYMBOLS = {
     "ttmpc_last_error": (C.c_char_p, []),
     "ttmpc_exit_status_name": (C.c_char_p, [_I]),
     "ttmpc_version": (_I, []),
+    "ttmpc_set_device": (_I, [_I]),
+    "ttmpc_get_device": (_I, [C.POINTER(C.c_int)]),
     "ttmpc_solve_batch_device": (_I, [_CFG, _I, _VP, _I, _I, _VP, _RES, _VP]),
     "ttmpc_solve_batch_host": (_I, [_CFG, _I, _VP, _I, _I, _VP, _RES]),
     "ttmpc_eval_batch_device": (_I, [_CFG, _I] + [_VP] * 10),

@@ -29,6 +29,12 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 extern "C" const char *ttmpc_last_error(void) { return g_err.c_str(); }
 extern "C" int ttmpc_version(void) { return TTMPC_VERSION; }
+extern "C" int ttmpc_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return TTMPC_OK; }
+extern "C" int ttmpc_get_device(int *device) {
+  if (!device) return fail(TTMPC_ERR_BAD_ARG, "null output");
+  CUDA_TRY(cudaGetDevice(device));
+  return TTMPC_OK;
+}
 extern "C" const char *ttmpc_exit_status_name(int code) {
   switch (code) {
     case TTMPC_CONVERGED: return "Converged";
@@ -138,6 +144,7 @@ struct Slot {
   int *h_ready = nullptr;         // pinned: one value per chunk
   cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
   cudaEvent_t ev_inputs = nullptr;
+  cudaEvent_t ev_done = nullptr;  // blocking-sync event: the host thread sleeps instead of spinning
   int *order = nullptr; size_t order_ints = 0;  // dispatch order + ranking scratch
   // device staging for the host API
   void *dbuf = nullptr; size_t dbytes = 0;
@@ -234,6 +241,7 @@ static int acquire_host_slot(Workspace **wout, Slot **out, int *busy_calls) {
   CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&s->exec_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&s->ev_inputs, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
   *out = s;
   return TTMPC_OK;
 }
@@ -247,6 +255,15 @@ struct HostSlotLease {  // returns the slot when the host call ends, whatever th
   }
 };
 }  // namespace
+// Wait for a stream of the host path.  Large batches take milliseconds: the thread sleeps on a
+// blocking-sync event (several calls are usually in flight, one spinning thread each would eat the
+// cores the other ranks and the staging threads need); small batches spin for the lowest latency.
+static int wait_stream(Slot *s, cudaStream_t st, int n_scenes) {
+  if (n_scenes < 512) { CUDA_TRY(cudaStreamSynchronize(st)); return TTMPC_OK; }
+  CUDA_TRY(cudaEventRecord(s->ev_done, st));
+  CUDA_TRY(cudaEventSynchronize(s->ev_done));
+  return TTMPC_OK;
+}
 static int ensure_dyn(Slot *w, size_t bytes) {
   if (bytes <= w->dyn_bytes) return TTMPC_OK;
   if (w->dyn_scratch) CUDA_TRY(cudaFree(w->dyn_scratch));
@@ -645,11 +662,13 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   }
   int timed_out = 0;
   if (stream_in) {
-    CUDA_TRY(cudaStreamSynchronize(st));
+    rc = wait_stream(w, st, n);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpy(&timed_out, w->ready + 1, sizeof(int), cudaMemcpyDeviceToHost));
   }
   if (!stream_in || timed_out) {  // unstreamed (re-)run: all inputs are resident now
-    CUDA_TRY(cudaStreamSynchronize(cs));
+    rc = wait_stream(w, cs, n);
+    if (rc) return rc;
     if (use_u0) CUDA_TRY(cudaMemcpyAsync(du, hu, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
     if (use_y0 && res->y) CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double) * nn * nu, cudaMemcpyHostToDevice, st));
     rc = solve_device_impl(cfg, n, dp, use_u0, use_y0 && res->y, h_c0 ? dc0 : nullptr, &dres, st, w, false);
@@ -659,7 +678,8 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   const size_t out_begin = (size_t)((char *)du - (char *)w->dbuf);
   CUDA_TRY(cudaMemcpyAsync((char *)w->hbuf + out_begin, (char *)w->dbuf + out_begin, cv.off - out_begin,
                            cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  rc = wait_stream(w, st, n);
+  if (rc) return rc;
   std::memcpy(res->u, hu, sizeof(double) * nn * nu);
   if (res->y) std::memcpy(res->y, hy, sizeof(double) * nn * nu);
   if (res->cost) std::memcpy(res->cost, hcost, sizeof(double) * nn);

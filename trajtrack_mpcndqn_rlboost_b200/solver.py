@@ -90,6 +90,10 @@ class BatchSolver:
         assert self.np == self.lib.ttmpc_num_params(C.byref(cfg))
         self.nu = cfg.nu * cfg.N_hor
         self.n1 = 2 * cfg.N_hor
+        # the CUDA device of the constructing thread; host calls from other threads (run_many) switch
+        # their thread to it first -- a new thread starts on device 0
+        dev = C.c_int(-1)
+        self.device = dev.value if self.lib.ttmpc_get_device(C.byref(dev)) == 0 else -1
 
     # -------------------------------------------------------------- host buffers
     def run(self, p, initial_guess=None, initial_lagrange_multipliers=None,
@@ -116,6 +120,8 @@ class BatchSolver:
                           penalty=_ptr(out["pen"]), y=_ptr(y), pred_states=_ptr(out["pred"]),
                           evals=_ptr(out["evals"]))
         t0 = time.perf_counter()
+        if self.device >= 0:
+            _lib.check(self.lib.ttmpc_set_device(self.device), "ttmpc_set_device")
         rc = self.lib.ttmpc_solve_batch_host(C.byref(self.cfg), n, _ptr(p),
                                              int(initial_guess is not None),
                                              int(initial_lagrange_multipliers is not None),
@@ -179,9 +185,16 @@ class BatchSolver:
                           last_fpr=dp(bufs["fpr"]), f1_infeas=dp(bufs["f1"]), f2_norm=dp(bufs["f2"]),
                           penalty=dp(bufs["pen"]), y=dp(bufs["y"]), pred_states=dp(bufs["pred"]),
                           evals=dp(bufs["evals"]))
-        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        st = torch.cuda.current_stream(p.device).cuda_stream if stream is None else stream
+        # the library works on the calling thread's current device: make that p's device for the call
+        prev = C.c_int(-1)
+        self.lib.ttmpc_get_device(C.byref(prev))
+        if prev.value != p.device.index:
+            _lib.check(self.lib.ttmpc_set_device(p.device.index), "ttmpc_set_device")
         rc = self.lib.ttmpc_solve_batch_device(C.byref(self.cfg), n, p.data_ptr(), int(use_u0),
                                                int(use_y0), dp(c0), C.byref(res), C.c_void_p(st))
+        if prev.value >= 0 and prev.value != p.device.index:
+            self.lib.ttmpc_set_device(prev.value)
         _lib.check(rc, "ttmpc_solve_batch_device")
         return BatchSolution(bufs["u"], bufs["cost"], bufs["exit_status"], bufs["outer"],
                              bufs["inner"], bufs["fpr"], bufs["f1"], bufs["f2"], bufs["pen"],
