@@ -123,14 +123,16 @@ def run_reference_arm(args):
     if rank != 0:
         return
     from tests import oracle_lib as O
-    cfg, p, w = build_workload(args.workload, 0, 1)
+    R = max(1, args.batches)
+    cfg, p0, w = build_workload(args.workload, 0, 1, 0)
+    ps = [p0] + [build_workload(args.workload, 0, 1, j)[1] for j in range(1, R)]  # the batches the GPU arm rotates through
     cores = os.cpu_count() or 1
-    sample = min(len(p), args.cpu_sample)
+    sample = min(len(p0), args.cpu_sample)
     O.load()
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        O.solve_batch(cfg, p[:sample], threads=cores, warp=False)
+        O.solve_batch(cfg, ps[it % R][:sample], threads=cores, warp=False)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -145,7 +147,7 @@ def run_reference_arm(args):
                    "note": "OpEn is Rust and absent here: CPU port (oracle, reference operation "
                            "order) on all host cores; each step = a bounded sample of the workload"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                         "sample": f"first {sample} scenes of {args.workload}, pthreads"},
+                         "sample": f"first {sample} scenes of each of the {R} rotating {args.workload} batches, pthreads"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
