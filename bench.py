@@ -358,7 +358,7 @@ def main():
                        "Nstcobs": cfg.Nstcobs, "Ndynobs": cfg.Ndynobs, "static_per_scene": w["n_static"],
                        "dynamic_per_scene": w["n_dynamic"], "max_inner": cfg.max_inner_iterations,
                        "max_outer": cfg.max_outer_iterations,
-                       "pipeline_depth": D,
+                       "pipeline_depth": D, "warmup_steps_run": warm,
                        "inputs": f"{R} distinct resident batches of {p_host.nbytes / 1e6:.0f} MB rotate through the steps "
                                  f"({R * p_host.nbytes / 1e6:.0f} MB > 126 MB L2): no step finds its inputs in L2",
                        "timing": "one CUDA-event pair around all K steps (up to pipeline_depth batches in flight, "
