@@ -236,12 +236,16 @@ static int acquire_host_slot(Workspace **wout, Slot **out, int *busy_calls) {
   Slot *s;
   rc = new_slot(w, &s);
   if (rc) return rc;
+  // a slot becomes a host slot only once everything it needs exists (a half-built one stays an
+  // unbound device slot, which needs none of this)
+  cudaError_t e = cudaHostAlloc(&s->h_ready, sizeof(int) * 4096, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->exec_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_inputs, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming | cudaEventBlockingSync);
+  if (e != cudaSuccess)
+    return fail(TTMPC_ERR_CUDA, std::string("host path: streams / pinned memory of a new slot: ") + cudaGetErrorString(e));
   s->host = true; s->host_busy = true;
-  CUDA_TRY(cudaHostAlloc(&s->h_ready, sizeof(int) * 4096, cudaHostAllocDefault));
-  CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&s->exec_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&s->ev_inputs, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
   *out = s;
   return TTMPC_OK;
 }
