@@ -28,6 +28,16 @@
 // Unroll policy of the hot loops.  The kernel is bound by instruction-cache refills (DESIGN.md
 // section 6), so every unroll factor is a trade between dependent-issue latency and code bytes;
 // -DTTMPC_SMALL_CODE builds the variant with every hot loop rolled.
+// Round-2 experiment (off by default, the default build is unchanged): -DTTMPC_COLD_OUTLINE keeps
+// the per-scene code (staging, helper service loop) out of the kernel body so that the
+// per-iteration code is contiguous; measure with tools/variants_r2.sh.
+#ifdef TTMPC_COLD_OUTLINE
+#define TT_COLD_INLINE static __noinline__
+#define TT_COLD_TPL __noinline__
+#else
+#define TT_COLD_INLINE inline
+#define TT_COLD_TPL
+#endif
 #ifdef TTMPC_SMALL_CODE
 #define TT_UNROLL_SCAN _Pragma("unroll 1")
 #define TT_UNROLL_2 _Pragma("unroll 1")
@@ -443,7 +453,7 @@ __device__ inline void stage_part2(const DevCfg &g, const WarpSmem &sm, const do
 // ~35 us per scene, 1 % of an average solve: measured with -DTTMPC_PROFILE_STAGE, tools/stage_profile.py).
 // A cp.async.bulk landing zone in the (then empty) L-BFGS ring was tried and dropped: part 2 is
 // bound by its 300 sincos + 1200 divisions, not by the loads, and its 14.4 KB block does not fit the ring.
-__device__ inline void stage_scene(const DevCfg &g, const WarpSmem &sm, const double *p,
+__device__ TT_COLD_INLINE void stage_scene(const DevCfg &g, const WarpSmem &sm, const double *p,
                                    double *dyn_scratch, int lane) {
 #ifdef TTMPC_PROFILE_STAGE
   const long long td0 = clock64();

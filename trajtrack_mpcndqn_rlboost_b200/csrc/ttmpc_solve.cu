@@ -460,7 +460,7 @@ __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z,
 // Serve owner m (helper slot already taken) until its current scene ends.
 // false = nothing happened for 3 s (the caller gives up helping).
 template <class DM>
-__device__ bool serve_owner(const DevCfg &g, CtaHelp *cta, unsigned char *smem_raw, int m, int epoch_m,
+__device__ TT_COLD_TPL bool serve_owner(const DevCfg &g, CtaHelp *cta, unsigned char *smem_raw, int m, int epoch_m,
                             const WarpSmem &mine, int lane) {
   unsigned char *base_m = smem_raw + (size_t)m * g.smem_per_warp;
   const WarpSmem own = carve<DM>(base_m, g);
