@@ -347,6 +347,25 @@ def main():
         cpu = {"value": sample / dt, "unit": "solves/s", "cores": cores, "kind": "port",
                "sample": f"first {sample} scenes of {args.workload}, {dt:.1f} s, pthreads"}
 
+    # ---------------- plan latency (the second half of BASELINE's metric): one scene per call on the
+    # device (the drop-in Solver.run use), next to the latency of one whole batch measured above
+    latency = {"batch_of_%d_ms" % n: seq_step_ms}
+    try:
+        one = solver.alloc_device(1, device=dev)
+        ts = []
+        for i in range(48):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(main_stream)
+            solver.run_device(p_devs[0][i:i + 1], one)
+            b.record(main_stream)
+            torch.cuda.synchronize()
+            if i >= 8:
+                ts.append(a.elapsed_time(b))
+        ts.sort()
+        latency.update({"one_scene_p50_ms": ts[len(ts) // 2], "one_scene_max_ms": ts[-1], "one_scene_samples": len(ts)})
+    except Exception as e:  # a diagnostic must never cost the bench line
+        latency["one_scene_error"] = repr(e)
+
     if rank == 0:
         info = solver.launch_info(n)
         line = {
@@ -376,6 +395,7 @@ def main():
             # per step: solve_kernel, plus rank_scenes_kernel + order_scenes_kernel when the batch
             # is larger than the resident warps (dispatch order)
             "gpu_launches": args.steps * (3 if n > info["grid"] * info["block"] // 32 else 1),
+            "plan_latency": latency,
             "clocks": summarize_clocks(samples),
             "roofline": roofline,
             "cpu_baseline": cpu,
