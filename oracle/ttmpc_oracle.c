@@ -775,6 +775,10 @@ static void f_grad(prob_t *pb, const double *u, double *out) {
   pb->n_grad++;
 }
 static int g_warp_mode = 0; /* set per solve; the vector helpers and L-BFGS read it */
+/* a*b + c.  The CUDA kernel fuses these products (explicit fma(), mirrored in WARP order); Rust
+ * never contracts a multiply-add, so the REFERENCE order rounds the product first, exactly like
+ * OpEn's `*u - gamma * *grad`, `u - temp_ * fpr - tau * dir`, `out[i] += s * a[i]`. */
+static double mad(double a, double b, double c) { return g_warp_mode ? fma(a, b, c) : a * b + c; }
 /* og.constraints.Rectangle(umin, umax) (mpc_generator.py:245-247) */
 static void project_u(const ttmpc_config *g, double *u) {
   for (int k = 0; k < g->N_hor; k++) {
@@ -808,17 +812,7 @@ typedef struct {
   double s[MAXMEM + 1][MAXNU], y[MAXMEM + 1][MAXNU];
   double rho[MAXMEM + 1], alpha[MAXMEM];
   double old_state[MAXNU], old_g[MAXNU];
-  /* WARP order only: Gram matrices of the compact form (csrc/ttmpc_solve.cu) */
-  double gsy[MAXMEM + 1][MAXMEM + 1], gyy[MAXMEM + 1][MAXMEM + 1];
 } lbfgs_t;
-
-/* mirror of row_dot(): N steps of (x, y) pairs, four interleaved accumulators */
-static double row_dot(const double *a, const double *b, int N) {
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int k = 0; k < N; k++)
-    acc[k & 3] = fma(a[2 * k + 1], b[2 * k + 1], fma(a[2 * k], b[2 * k], acc[k & 3]));
-  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
-}
 
 static int lb_idx(const lbfgs_t *l, int i) { return (l->head + i) % (l->mem + 1); }
 static void lb_init(lbfgs_t *l, int n, int mem) {
@@ -828,50 +822,23 @@ static void lb_init(lbfgs_t *l, int n, int mem) {
   l->cbfgs_alpha = 1.0; l->cbfgs_eps = 1e-8; l->sy_eps = 1e-10;
 }
 static void lb_reset(lbfgs_t *l) { l->active = 0; l->first_old = 1; }
-/* compact (Gram) form of the same operator, operation order of the CUDA kernel */
-static void lb_apply_gram(lbfgs_t *l, double *q) {
-  const int m = l->active, N = l->n / 2;
-  double t[MAXMEM], w[MAXMEM], a[MAXMEM], cc[MAXMEM];
-  for (int i = 0; i < m; i++) {
-    t[i] = row_dot(l->s[lb_idx(l, i)], q, N);
-    w[i] = row_dot(l->y[lb_idx(l, i)], q, N);
-  }
-  for (int c = 0; c < m; c++) {
-    a[c] = l->rho[lb_idx(l, c)] * t[c];
-    for (int i = c + 1; i < m; i++) t[i] = fma(-a[c], l->gsy[lb_idx(l, i)][lb_idx(l, c)], t[i]);
-  }
-  for (int i = 0; i < m; i++) {
-    for (int c = 0; c < m; c++) w[i] = fma(-a[c], l->gyy[lb_idx(l, i)][lb_idx(l, c)], w[i]);
-    w[i] = l->gamma * w[i];
-  }
-  for (int c = m - 1; c >= 0; c--) {
-    cc[c] = a[c] - l->rho[lb_idx(l, c)] * w[c];
-    for (int i = 0; i < c; i++) w[i] = fma(cc[c], l->gsy[lb_idx(l, c)][lb_idx(l, i)], w[i]);
-  }
-  for (int e = 0; e < l->n; e++) {
-    double d = l->gamma * q[e];
-    for (int c = 0; c < m; c++) d = fma(-(l->gamma * a[c]), l->y[lb_idx(l, c)][e], d);
-    for (int c = m - 1; c >= 0; c--) d = fma(cc[c], l->s[lb_idx(l, c)][e], d);
-    q[e] = d;
-  }
-}
-
+/* lbfgs crate apply_hessian: the literal two-loop recursion.  The CUDA kernel runs exactly this
+ * (csrc/ttmpc_solve.cu lbfgs_apply); in WARP order dot() is the butterfly all-reduce and mad() fuses. */
 static void lb_apply(lbfgs_t *l, double *q) {
   if (l->active == 0) return;
-  if (g_warp_mode) { lb_apply_gram(l, q); return; }
   const int n = l->n;
   for (int i = 0; i < l->active; i++) {
     int k = lb_idx(l, i);
     double a = l->rho[k] * dot(n, l->s[k], q);
     l->alpha[i] = a;
-    for (int t = 0; t < n; t++) q[t] = fma(-a, l->y[k][t], q[t]);
+    for (int t = 0; t < n; t++) q[t] = mad(-a, l->y[k][t], q[t]);
   }
   for (int t = 0; t < n; t++) q[t] *= l->gamma;
   for (int i = l->active - 1; i >= 0; i--) {
     int k = lb_idx(l, i);
     double beta = l->rho[k] * dot(n, l->y[k], q);
     double cf = l->alpha[i] - beta;
-    for (int t = 0; t < n; t++) q[t] = fma(cf, l->s[k][t], q[t]);
+    for (int t = 0; t < n; t++) q[t] = mad(cf, l->s[k][t], q[t]);
   }
 }
 /* returns 1 if accepted; norm_g = |g| (the caller already has it) */
@@ -905,16 +872,6 @@ static int lb_update(lbfgs_t *l, const double *g, const double *state, double no
   int k0 = lb_idx(l, 0);
   l->gamma = (1.0 / l->rho[k0]) / yy;
   l->active = (l->mem < l->active + 1) ? l->mem : l->active + 1;
-  if (g_warp_mode) { /* Gram row / column of the new pair */
-    const int N = n / 2;
-    l->gsy[k0][k0] = ys; l->gyy[k0][k0] = yy;
-    for (int i = 1; i < l->active; i++) {
-      int pl = lb_idx(l, i);
-      l->gsy[k0][pl] = row_dot(l->s[k0], l->y[pl], N);
-      l->gsy[pl][k0] = row_dot(l->s[pl], l->y[k0], N);
-      l->gyy[k0][pl] = l->gyy[pl][k0] = row_dot(l->y[k0], l->y[pl], N);
-    }
-  }
   return 1;
 }
 
@@ -950,11 +907,11 @@ static void pc_set_akkt(panoc_t *c, double tol) {
 static int pc_exit(const panoc_t *c) {
   if (!(c->norm_fpr < c->tolerance)) return 0;
   double r[MAXNU];
-  for (int i = 0; i < c->n; i++) r[i] = fma(c->gamma, c->grad[i] - c->grad_prev[i], c->fpr[i]);
+  for (int i = 0; i < c->n; i++) r[i] = mad(c->gamma, c->grad[i] - c->grad_prev[i], c->fpr[i]);
   return sqrt(dot(c->n, r, r)) < c->akkt_tol;
 }
 static void pe_gradient_step(panoc_t *c, const double *u) {
-  for (int i = 0; i < c->n; i++) c->gstep[i] = fma(-c->gamma, c->grad[i], u[i]);
+  for (int i = 0; i < c->n; i++) c->gstep[i] = mad(-c->gamma, c->grad[i], u[i]);
 }
 static void pe_half_step(panoc_t *c, const ttmpc_config *g) {
   memcpy(c->u_half, c->gstep, c->n * sizeof(double));
@@ -1012,10 +969,10 @@ static void pe_update_lipschitz(panoc_t *c, prob_t *pb, const double *u) {
 static int pe_ls_condition(panoc_t *c, prob_t *pb, const double *u) {
   const int n = c->n;
   const double tau = c->tau, one_m = 1.0 - tau;
-  for (int i = 0; i < n; i++) c->u_plus[i] = fma(-tau, c->dir[i], fma(-one_m, c->fpr[i], u[i]));
+  for (int i = 0; i < n; i++) c->u_plus[i] = mad(-tau, c->dir[i], mad(-one_m, c->fpr[i], u[i]));
   f_cost(pb, c->u_plus, &c->cost);
   f_grad(pb, c->u_plus, c->grad);
-  for (int i = 0; i < n; i++) c->gstep[i] = fma(-c->gamma, c->grad[i], c->u_plus[i]);
+  for (int i = 0; i < n; i++) c->gstep[i] = mad(-c->gamma, c->grad[i], c->u_plus[i]);
   pe_half_step(c, pb->g);
   const double dd = norm2sq_diff(n, c->u_half, c->gstep), g2 = dot(n, c->grad, c->grad);
   c->lhs_ls = c->cost - 0.5 * c->gamma * g2 + 0.5 * dd / c->gamma;

@@ -19,6 +19,6 @@ if len(sys.argv) > 3:
     it = bufs["inner"].sum().item()
     print(json.dumps(dict(bps=os.environ.get("TTMPC_MAX_BLOCKS_PER_SM"), helpers=os.environ.get("TTMPC_NO_HELPERS"), ms=min(ms[2:]), iters=it, info=s.launch_info(n))))
 else:
-    for bps in ("1", "2", "3"):
+    for bps in os.environ.get("OCC_LIST", "1,2,3,4").split(","):
         env = dict(os.environ, TTMPC_MAX_BLOCKS_PER_SM=bps, TTMPC_NO_HELPERS="1")
         subprocess.run([sys.executable, __file__, sys.argv[1], sys.argv[2], "child"], env=env)

@@ -49,6 +49,16 @@
 #define TT_UNROLL_4 _Pragma("unroll 4")
 #endif
 
+// Code-factoring switches (round 2).  The solve kernel is bound by instruction-cache refills: 8-12
+// warps per SM walk a ~39 KB hot loop out of phase through a 32 KB cache.  Each bit moves one
+// family of repeated code out of line into ONE shared copy (a few call instructions instead of an
+// inlined body per use): fewer distinct cache lines at the price of call overhead and less
+// interleaving.  Same operations in the same order either way (bit-identical results); the
+// default is what measured fastest on the B200 (profiles/r2_*).
+//   1 sincos   2 scans   4 divisions / square roots   8 the 4-value reduction of eval_psi
+#ifndef TT_FACTOR
+#define TT_FACTOR 0
+#endif
 namespace ttmpc {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -96,45 +106,187 @@ __host__ __device__ __forceinline__ void tt_sincos(double x, double *s, double *
   *s = so; *c = co;
 }
 
+// Same function for the hot path (eval_psi): the coefficients come from the constant bank, so
+// every DFMA takes its constant as an operand.  With literals ptxas materialises each 64-bit
+// constant with two UMOVs -- 28 of the 85 instructions of one inlined tt_sincos, three of them per
+// evaluation.  Identical operations in identical order: bit-identical results.
+static __constant__ double TT_SC[16] = {
+    6.36619772367581382433e-01, 1.5707963267948966e+00, 6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__device__ __forceinline__ void tt_sincos_c(double x, double *s, double *c) {
+  const double kd = rint(x * TT_SC[0]);
+  double r = fma(-kd, TT_SC[1], x);
+  r = fma(-kd, TT_SC[2], r);
+  r = fma(-kd, TT_SC[3], r);
+  const int q = (int)((long long)kd & 3);
+  const double z = r * r;
+  double ps = fma(z, TT_SC[4], TT_SC[5]);
+  ps = fma(z, ps, TT_SC[6]);
+  ps = fma(z, ps, TT_SC[7]);
+  ps = fma(z, ps, TT_SC[8]);
+  ps = fma(z, ps, TT_SC[9]);
+  const double sr = fma(r * z, ps, r);
+  double pc = fma(z, TT_SC[10], TT_SC[11]);
+  pc = fma(z, pc, TT_SC[12]);
+  pc = fma(z, pc, TT_SC[13]);
+  pc = fma(z, pc, TT_SC[14]);
+  pc = fma(z, pc, TT_SC[15]);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const bool swap = (q & 1) != 0;
+  const double sb = swap ? cr : sr, cb = swap ? sr : cr;
+  double so = (q & 2) ? -sb : sb, co = ((q + 1) & 2) ? -cb : cb;
+  if (!(fabs(x) < 1.0e9)) { so = x * 0.0 + NAN; co = so; }  // huge / non-finite argument
+  *s = so; *c = co;
+}
+
+#if TT_FACTOR & 1
+struct SC2 { double s, c; };
+static __device__ __noinline__ SC2 tt_sincos_call(double x) { SC2 r; tt_sincos_c(x, &r.s, &r.c); return r; }
+__device__ __forceinline__ void tt_sincos_hot(double x, double *s, double *c) { const SC2 r = tt_sincos_call(x); *s = r.s; *c = r.c; }
+#elif TT_FACTOR & 16
+__device__ __forceinline__ void tt_sincos_hot(double x, double *s, double *c) { tt_sincos(x, s, c); }
+#else
+__device__ __forceinline__ void tt_sincos_hot(double x, double *s, double *c) { tt_sincos_c(x, s, c); }
+#endif
+// IEEE division / square root: ~15 inlined instructions per use (MUFU seed, Newton steps, range
+// check, slow-path call); the PANOC step has a dozen of them
+#if TT_FACTOR & 4
+static __device__ __noinline__ double tt_div(double a, double b) { return a / b; }
+static __device__ __noinline__ double tt_sqrt(double a) { return sqrt(a); }
+#else
+__device__ __forceinline__ double tt_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double tt_sqrt(double a) { return sqrt(a); }
+#endif
+
 // ---------------------------------------------------------------- warp utils
-static __device__ __noinline__ double wsum(double v) {
-TT_UNROLL_SCAN
+// Hand-written shuffle primitives.  Round 1 left these to the compiler as rolled loops in
+// __noinline__ functions to save instruction-cache bytes; the SASS of one rolled scan level was
+// 20 instructions for two doubles (4 SHFL + 4 MOV + 2 DADD + 4 FSEL + loop / divergence-check
+// overhead) and the moves in and out of the reduction functions were 15 % of all executed
+// instructions (profiles/r2_*).  The versions below issue fewer instructions AND are not longer:
+//  * scans use the shuffle's own "source lane in range" predicate to gate the add (no compare);
+//  * all-reduces of several values do a reduce-scatter over the first levels (lanes keep half of
+//    the values, send the other half), a butterfly over the rest and an all-gather: 10 double
+//    shuffles instead of 20 for four values.  Every value still goes through the SAME addition
+//    tree as in a plain xor-butterfly (x + y == y + x bit for bit), so results are unchanged and
+//    the CPU oracle's w_sum() mirror stays valid.
+template <int O>
+__device__ __forceinline__ void up_add(double &v) {  // v += v[lane - O] on lanes >= O
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tl, th;\n\t.reg .f64 t;\n\t"
+               "mov.b64 {lo, hi}, %0;\n\t"
+               "shfl.sync.up.b32 tl|p, lo, %1, 0, 0xffffffff;\n\t"
+               "shfl.sync.up.b32 th, hi, %1, 0, 0xffffffff;\n\t"
+               "mov.b64 t, {tl, th};\n\t"
+               "@p add.rn.f64 %0, %0, t;\n\t}"
+               : "+d"(v) : "n"(O));
+}
+template <int O>
+__device__ __forceinline__ void down_add(double &v) {  // v += v[lane + O] on lanes < 32 - O
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tl, th;\n\t.reg .f64 t;\n\t"
+               "mov.b64 {lo, hi}, %0;\n\t"
+               "shfl.sync.down.b32 tl|p, lo, %1, 31, 0xffffffff;\n\t"
+               "shfl.sync.down.b32 th, hi, %1, 31, 0xffffffff;\n\t"
+               "mov.b64 t, {tl, th};\n\t"
+               "@p add.rn.f64 %0, %0, t;\n\t}"
+               : "+d"(v) : "n"(O));
+}
+#if TT_FACTOR & 2
+#define TT_SCAN_FN static __device__ __noinline__
+#else
+#define TT_SCAN_FN __device__ __forceinline__
+#endif
+struct D2 { double a, b; };
+// inclusive prefix sum over lanes (Kogge-Stone)
+TT_SCAN_FN double wscan(double v, int) {
+  up_add<1>(v); up_add<2>(v); up_add<4>(v); up_add<8>(v); up_add<16>(v);
+  return v;
+}
+TT_SCAN_FN D2 wscan2v(double a, double b) {  // two scans, interleaved
+  up_add<1>(a); up_add<1>(b); up_add<2>(a); up_add<2>(b); up_add<4>(a); up_add<4>(b);
+  up_add<8>(a); up_add<8>(b); up_add<16>(a); up_add<16>(b);
+  D2 r; r.a = a; r.b = b;
+  return r;
+}
+__device__ __forceinline__ void wscan2(double &a, double &b) { const D2 r = wscan2v(a, b); a = r.a; b = r.b; }
+// inclusive suffix sum over lanes
+TT_SCAN_FN double wsuffix(double v, int) {
+  down_add<1>(v); down_add<2>(v); down_add<4>(v); down_add<8>(v); down_add<16>(v);
+  return v;
+}
+TT_SCAN_FN D2 wsuffix2v(double a, double b) {
+  down_add<1>(a); down_add<1>(b); down_add<2>(a); down_add<2>(b); down_add<4>(a); down_add<4>(b);
+  down_add<8>(a); down_add<8>(b); down_add<16>(a); down_add<16>(b);
+  D2 r; r.a = a; r.b = b;
+  return r;
+}
+__device__ __forceinline__ void wsuffix2(double &a, double &b) { const D2 r = wsuffix2v(a, b); a = r.a; b = r.b; }
+// all-reduce of one value: xor-butterfly, offsets 16 .. 1
+__device__ __forceinline__ double wsum_inl(double v) {
+#pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+static __device__ __noinline__ double wsum(double v) { return wsum_inl(v); }
+// all-reduce of two values: 7 double shuffles instead of 10
+__device__ __forceinline__ void wsum2_inl(double &a, double &b, int lane) {
+  const bool b4 = (lane & 16) != 0;
+  double x = b4 ? b : a;
+  const double sx = b4 ? a : b;
+  x += __shfl_xor_sync(FULL, sx, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+  a = __shfl_sync(FULL, x, 0); b = __shfl_sync(FULL, x, 16);
+}
+// all-reduce of four values: 10 double shuffles instead of 20
+__device__ __forceinline__ void wsum4_inl(double &a, double &b, double &c, double &d, int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+  double x = b4 ? c : a, y = b4 ? d : b;
+  const double sx = b4 ? a : c, sy = b4 ? b : d;
+  x += __shfl_xor_sync(FULL, sx, 16); y += __shfl_xor_sync(FULL, sy, 16);
+  double z = b3 ? y : x;
+  const double sz = b3 ? x : y;
+  z += __shfl_xor_sync(FULL, sz, 8);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) z += __shfl_xor_sync(FULL, z, o);
+  a = __shfl_sync(FULL, z, 0); b = __shfl_sync(FULL, z, 8);
+  c = __shfl_sync(FULL, z, 16); d = __shfl_sync(FULL, z, 24);
+}
 struct D3 { double a, b, c; };
+struct D4 { double a, b, c, d; };
+static __device__ __noinline__ D2 wsum2v(double a, double b) {
+  wsum2_inl(a, b, threadIdx.x & 31);
+  D2 r; r.a = a; r.b = b;
+  return r;
+}
 static __device__ __noinline__ D3 wsum3v(double a, double b, double c) {
-TT_UNROLL_SCAN
-  for (int o = 16; o > 0; o >>= 1) {
-    double ta = __shfl_xor_sync(FULL, a, o);
-    double tb = __shfl_xor_sync(FULL, b, o);
-    double tc = __shfl_xor_sync(FULL, c, o);
-    a += ta; b += tb; c += tc;
-  }
+  double d = 0.0;
+  wsum4_inl(a, b, c, d, threadIdx.x & 31);
   D3 r; r.a = a; r.b = b; r.c = c;
   return r;
+}
+#if TT_FACTOR & 8
+static __device__ __noinline__ D4 wsum4v(double a, double b, double c, double d) {
+  wsum4_inl(a, b, c, d, threadIdx.x & 31);
+  D4 r; r.a = a; r.b = b; r.c = c; r.d = d;
+  return r;
+}
+__device__ __forceinline__ void wsum4(double &a, double &b, double &c, double &d, int) {
+  const D4 r = wsum4v(a, b, c, d);
+  a = r.a; b = r.b; c = r.c; d = r.d;
+}
+#else
+__device__ __forceinline__ void wsum4(double &a, double &b, double &c, double &d, int lane) { wsum4_inl(a, b, c, d, lane); }
+#endif
+__device__ __forceinline__ void wsum2(double &a, double &b) {
+  const D2 r = wsum2v(a, b);
+  a = r.a; b = r.b;
 }
 __device__ __forceinline__ void wsum3(double &a, double &b, double &c) {
   const D3 r = wsum3v(a, b, c);
   a = r.a; b = r.b; c = r.c;
-}
-// inclusive prefix sum over lanes (Kogge-Stone)
-__device__ __forceinline__ double wscan(double v, int lane) {
-TT_UNROLL_SCAN
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_up_sync(FULL, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
-// inclusive suffix sum over lanes
-__device__ __forceinline__ double wsuffix(double v, int lane) {
-TT_UNROLL_SCAN
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_down_sync(FULL, v, o);
-    if (lane + o < 32) v += t;
-  }
-  return v;
 }
 __device__ __forceinline__ double clipd_ref(double z, double lo, double hi) {
   return fmin(fmax(z, lo), hi);
@@ -204,9 +356,6 @@ struct WarpSmem {
   float *dynb;    // [Ndyn][N][3] conservative fp32 bounding test: cx cy R2
   double2 *lbs;   // [(mem+1)][NP]  L-BFGS s rows; NP = N|1 (odd stride: rows read by
   double2 *lby;   // [(mem+1)][NP]  different lanes fall in different banks)
-  double2 *qrow;  // [NP]           vector the inverse Hessian is applied to
-  double *gsy;    // [(mem+1)][(mem+1)]  Gram matrix  s_p . y_q
-  double *gyy;    // [(mem+1)][(mem+1)]  Gram matrix  y_p . y_q
   double *rho;    // [mem+1]
   double *alpha;  // [2*(mem+1)]  gamma*a_c and (a_c - beta_c) of the last apply
   // mailbox of the tail helpers (see ttmpc_solve.cu): the owner's request / the helper's answer
@@ -251,8 +400,6 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, 
   b += (sizeof(float) * 3 * (size_t)Ndyn * N + 15) / 16 * 16;
   const int NP = N | 1;
   b += sizeof(double2) * (size_t)(mem + 1) * NP * 2;
-  b += sizeof(double2) * (size_t)NP;
-  b += sizeof(double) * (size_t)(mem + 1) * (mem + 1) * 2;
   b += sizeof(double) * ((mem + 2) / 2 * 2);
   b += sizeof(double) * (2 * (mem + 1));
   b += sizeof(double2) * 3 * (size_t)N + (sizeof(HelpHdr) + 15) / 16 * 16;  // mailbox rows + header
@@ -271,15 +418,12 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
   const int NP = N | 1;
   w.lbs = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(MEM + 1) * NP;
   w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(MEM + 1) * NP;
-  w.qrow = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)NP;
   w.fleet = reinterpret_cast<float2 *>(q); q += (sizeof(float2) * (size_t)Nother * N + 15) / 16 * 16;
   w.dynb = reinterpret_cast<float *>(q); q += (sizeof(float) * 3 * (size_t)Ndyn * N + 15) / 16 * 16;
   w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 6 * N;
   w.os = reinterpret_cast<double *>(q); q += sizeof(double) * ((Nstc * nstcobs + 1) / 2 * 2);
   w.D = reinterpret_cast<double *>(q); q += sizeof(double) * ((Ndyn + 1) / 2 * 2);
   w.vref = reinterpret_cast<double *>(q); q += sizeof(double) * ((N + 1) / 2 * 2);
-  w.gsy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(MEM + 1) * (MEM + 1);
-  w.gyy = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(MEM + 1) * (MEM + 1);
   w.rho = reinterpret_cast<double *>(q); q += sizeof(double) * ((MEM + 2) / 2 * 2);
   w.alpha = reinterpret_cast<double *>(q); q += sizeof(double) * (2 * (MEM + 1));
   w.hreq = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)N;
@@ -488,18 +632,6 @@ struct EvalOut {
   bool any_hard;
 };
 
-struct D4 { double a, b, c, d; };
-static __device__ __noinline__ D4 wsum4v(double a, double b, double c, double d) {
-TT_UNROLL_SCAN
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ta = __shfl_xor_sync(FULL, a, o), tb = __shfl_xor_sync(FULL, b, o);
-    const double tc = __shfl_xor_sync(FULL, c, o), td = __shfl_xor_sync(FULL, d, o);
-    a += ta; b += tb; c += tc; d += td;
-  }
-  D4 r; r.a = a; r.b = b; r.c = c; r.d = d;
-  return r;
-}
-
 // Evaluate psi (and its gradient when GRAD) at this lane's (v, w).
 // ya / yw are this lane's multipliers for the linear / angular acceleration rows.
 // DM carries the problem dimensions (compile-time for the default configuration).
@@ -543,20 +675,16 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   const double tha = cx->th0 + th_ex;
   const double thb = fma(0.5, tw, tha), thc = tha + tw;
   double sa, ca, sb, cb, sc, cc;
-  tt_sincos(tha, &sa, &ca);
-  tt_sincos(thb, &sb, &cb);
-  tt_sincos(thc, &sc, &cc);
+  tt_sincos_hot(tha, &sa, &ca);
+  tt_sincos_hot(thb, &sb, &cb);
+  tt_sincos_hot(thc, &sc, &cc);
   const double Cs = fma(4.0, cb, ca) + cc, Ss = fma(4.0, sb, sa) + sc;
   const double hv = g.h6 * v;
   const double dx = hv * Cs, dy = hv * Ss;
   double X, Y;
   {  // two prefix scans, interleaved
     double a = dx, b = dy;
-TT_UNROLL_SCAN
-    for (int o = 1; o < 32; o <<= 1) {
-      const double ta = __shfl_up_sync(FULL, a, o), tb = __shfl_up_sync(FULL, b, o);
-      if (lane >= o) { a += ta; b += tb; }
-    }
+    wscan2(a, b);
     X = cx->x0 + a; Y = cx->y0 + b;
   }
   const double TH = cx->th0 + th_in;
@@ -810,7 +938,7 @@ TT_UNROLL_4
   double aa = (v - vp) * g.inv_ts, aw = (w - wp) * g.inv_ts, ea, ew, alm;
   {
     cost += fma(aw * aw, cx->wacc_pen, (aa * aa) * cx->acc_pen);
-    const double icm = 1.0 / fmax(c, 1.0);
+    const double icm = tt_div(1.0, fmax(c, 1.0));
     double z = fma(ya, icm, aa);
     ea = z - clipd(z, g.amin, g.amax);
     z = fma(yw, icm, aw);
@@ -880,11 +1008,7 @@ TT_UNROLL_4
     const double hvt = hv * ts;
     const double dxdw = -(hvt * fma(2.0, sb, sc)), dydw = hvt * fma(2.0, cb, cc);
     double lx = gx, ly = gy;
-TT_UNROLL_SCAN
-    for (int o = 1; o < 32; o <<= 1) {
-      const double ta = __shfl_down_sync(FULL, lx, o), tb = __shfl_down_sync(FULL, ly, o);
-      if (lane + o < 32) { lx += ta; ly += tb; }
-    }
+    wsuffix2(lx, ly);
     const double m = fma(ly, dx, -(lx * dy));
     const double lt = wsuffix(gt + m, lane) - m;
     // direct control terms
@@ -910,9 +1034,9 @@ TT_UNROLL_SCAN
   }
   EPROF(7)
   // ---- one batched reduction: f, ALM distance (and the line-search scalars)
-  const D4 r = wsum4v(cost, alm, ddp, g2p);
-  out.f = r.a; out.dd = r.c; out.g2 = r.d;
-  out.psi = r.a + c * r.b / 2 + c * f2sq / 2;
+  wsum4(cost, alm, ddp, g2p, lane);
+  out.f = cost; out.dd = ddp; out.g2 = g2p;
+  out.psi = cost + c * alm / 2 + c * f2sq / 2;
   EPROF(8)
   return out;
 }

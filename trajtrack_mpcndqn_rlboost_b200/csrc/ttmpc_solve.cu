@@ -73,95 +73,54 @@ __device__ __forceinline__ void project(const DevCfg &g, double a0, double a1, d
   o1 = clipd(a1, -g.wmax, g.wmax);
 }
 
-template <class DM>
-__device__ __forceinline__ int lb_slot(const DevCfg &g, const Uni &U, int i) {
-  int s = U.lb_head + i;
-  const int m1 = DM::mem(g) + 1;
-  return s >= m1 ? s - m1 : s;
-}
-
-// ---------------------------------------------------------------- L-BFGS, Gram form
-// Same quasi-Newton operator as the lbfgs crate's two-loop recursion (same pairs, same
-// C-BFGS acceptance test, same H0 = gamma I), evaluated in its compact form: the two
-// loops only need the inner products s_i.q, y_i.q, s_i.y_l, y_i.y_l.  The Gram matrices
-// are kept up to date when a pair is accepted, the products with q are computed in ONE
-// "lane-per-dot" pass (lane j walks row j sequentially, no shuffles), and the two
-// triangular recurrences run with one lane per row.  20 dependent warp reductions per
-// apply become one pass + 2m broadcasts.  The CPU oracle mirrors this operation order.
-
-// dot product of two smem rows of N double2, four interleaved accumulators
-static __device__ __noinline__ double row_dot(const double2 *a, const double2 *b, int N) {
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-  int k = 0;
-  for (; k + 3 < N; k += 4) {
-    const double2 a0 = a[k], b0 = b[k], a1 = a[k + 1], b1 = b[k + 1];
-    const double2 a2 = a[k + 2], b2 = b[k + 2], a3 = a[k + 3], b3 = b[k + 3];
-    acc0 = fma(a0.y, b0.y, fma(a0.x, b0.x, acc0));
-    acc1 = fma(a1.y, b1.y, fma(a1.x, b1.x, acc1));
-    acc2 = fma(a2.y, b2.y, fma(a2.x, b2.x, acc2));
-    acc3 = fma(a3.y, b3.y, fma(a3.x, b3.x, acc3));
-  }
-  for (; k < N; k++) {
-    const double2 av = a[k], bv = b[k];
-    const double t = fma(av.y, bv.y, fma(av.x, bv.x, (k & 3) == 0 ? acc0 : (k & 3) == 1 ? acc1 : (k & 3) == 2 ? acc2 : acc3));
-    if ((k & 3) == 0) acc0 = t; else if ((k & 3) == 1) acc1 = t; else if ((k & 3) == 2) acc2 = t; else acc3 = t;
-  }
-  return (acc0 + acc1) + (acc2 + acc3);
-}
-
-// lbfgs::update_hessian(g = fpr, state = u)
+// ---------------------------------------------------------------- L-BFGS, two-loop recursion
+// lbfgs crate (0.2.x) update_hessian / apply_hessian as OpEn's PANOCCache configures it: same
+// pairs, same C-BFGS acceptance test, same H0 = gamma I, the literal two-loop recursion with one
+// butterfly all-reduce per inner product.
+//
+// Round 1 ran the two loops in compact (Gram) form: half the dependent latency of one apply
+// (3.5 k instead of 7 k cycles), but 8 KB of hot code (Gram maintenance, lane-per-dot pass, two
+// triangular recurrences).  Round 2 measured what that costs with the GPU full: the hot loop of the
+// solve is walked by 8 warps per SM out of phase, every line of it missed the 32 KB instruction
+// cache once per pass, and removing the L-BFGS code alone (experiment, profiles/r2_c_*) took the
+// instruction-cache hit rate from 69 % to 94 % and the issue rate up by 43 %.  The literal recursion
+// is ~1.5 KB, executes fewer instructions (no Gram upkeep), and its reduction latency is hidden
+// by the other warps.  The CPU oracle's WARP order mirrors it (lb_apply with butterfly dots).
 template <class DM>
 __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm, Lane &z, Uni &U,
                                              int lane) {
   const int N = DM::N(g), NP = N | 1, MEM = DM::mem(g), M1 = MEM + 1;
-  if (U.lb_first) {
-    U.lb_first = 0;
-    z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
-    return;
-  }
   const double sv0 = z.u0 - z.os0, sv1 = z.u1 - z.os1;
   const double yv0 = z.f0 - z.og0, yv1 = z.f1 - z.og1;
-  double ys = pdot(sv0, sv1, yv0, yv1), ss = pdot(sv0, sv1, sv0, sv1), yy = pdot(yv0, yv1, yv0, yv1);
-  wsum3(ys, ss, yy);
-  const double rho = 1.0 / ys;
-  if (ss <= 2.2250738585072014e-308 || ys <= SY_EPSILON) return;
-  {
-    const double lhs = ys / ss;
+  bool accept = true;
+  double ys = 0.0, yy = 0.0;
+  if (!U.lb_first) {
+    double ss = pdot(sv0, sv1, sv0, sv1);
+    ys = pdot(sv0, sv1, yv0, yv1); yy = pdot(yv0, yv1, yv0, yv1);
+    wsum3(ys, ss, yy);
+    const double lhs = tt_div(ys, ss);
     const double rhs = CBFGS_EPSILON * U.norm_fpr;  // cbfgs_alpha = 1: pow(x, 1) == x
-    if (!(lhs > rhs && isfinite(lhs) && isfinite(rhs))) return;
+    accept = !(ss <= 2.2250738585072014e-308 || ys <= SY_EPSILON) &&
+             (lhs > rhs && isfinite(lhs) && isfinite(rhs));
   }
+  if (!accept) return;
   z.os0 = z.u0; z.os1 = z.u1; z.og0 = z.f0; z.og1 = z.f1;
+  if (U.lb_first) { U.lb_first = 0; return; }
   // rotate_right(1): scratch slot becomes slot 0
   U.lb_head = U.lb_head + MEM; if (U.lb_head >= M1) U.lb_head -= M1;
   const int k0 = U.lb_head;
+  const double rho = tt_div(1.0, ys);
   if (lane < N) {
     sm.lbs[k0 * NP + lane] = make_double2(sv0, sv1);
     sm.lby[k0 * NP + lane] = make_double2(yv0, yv1);
   }
-  if (lane == 0) { sm.rho[k0] = rho; sm.gsy[k0 * M1 + k0] = ys; sm.gyy[k0 * M1 + k0] = yy; }
-  U.lb_gamma = (1.0 / rho) / yy;
+  if (lane == 0) sm.rho[k0] = rho;
+  U.lb_gamma = tt_div(tt_div(1.0, rho), yy);
   U.lb_active = min(MEM, U.lb_active + 1);
-  __syncwarp();
-  // Gram row / column of the new pair against the older active pairs: 3 products per pair
-  const int K = 3 * (U.lb_active - 1);
-  for (int base = 0; base < K; base += 32) {
-    const int j = base + lane;
-    if (j < K) {
-      // one call for all three kinds of product (a divergent call would run three times)
-      const int l = 1 + j / 3, kind = j - 3 * (l - 1);
-      const int pl = lb_slot<DM>(g, U, l);
-      const double2 *ra = kind == 0 ? sm.lbs + k0 * NP : kind == 1 ? sm.lbs + pl * NP : sm.lby + k0 * NP;
-      const double2 *rb = kind == 1 ? sm.lby + k0 * NP : sm.lby + pl * NP;
-      const double v = row_dot(ra, rb, N);
-      double *dst = kind == 0 ? sm.gsy + k0 * M1 + pl : kind == 1 ? sm.gsy + pl * M1 + k0 : sm.gyy + k0 * M1 + pl;
-      *dst = v;
-      if (kind == 2) sm.gyy[pl * M1 + k0] = v;
-    }
-  }
   __syncwarp();
 }
 
-// lbfgs::apply_hessian on the direction, compact form (see above)
+// lbfgs::apply_hessian on the direction
 template <class DM>
 __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm, Lane &z,
                                             const Uni &U, int lane) {
@@ -169,66 +128,27 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   if (m == 0) return;
   const int N = DM::N(g), NP = N | 1, M1 = DM::mem(g) + 1;
   const bool act = lane < N;
-  if (act) sm.qrow[lane] = make_double2(z.d0, z.d1);
-  __syncwarp();
-  // lane l < m: s_l . q      lane m + l: y_l . q      (2m <= 32)
-  double dotv = 0.0;
-  if (lane < 2 * m) {
-    const int l = lane < m ? lane : lane - m;
-    const int pl = lb_slot<DM>(g, U, l);
-    dotv = row_dot((lane < m ? sm.lbs : sm.lby) + pl * NP, sm.qrow, N);
-  }
-  const double yq = __shfl_sync(FULL, dotv, (lane + m) & 31);
-  const int pme = lb_slot<DM>(g, U, lane < m ? lane : 0);  // this lane's row (lanes < m)
-  const double rho_me = sm.rho[pme];
-  // forward recurrence: a_c = rho_c t_c ; t_l -= a_c (s_l . y_c) for l > c
-  double t = dotv, a_me = 0.0;
+  const int lk = act ? lane : N - 1;
+  double q0 = z.d0, q1 = z.d1, a_me = 0.0;  // lane i keeps alpha_i
+  int k = U.lb_head;
 #pragma unroll 1
-  for (int c = 0; c < m; c++) {
-    const double a_c = __shfl_sync(FULL, rho_me * t, c);
-    if (lane == c) a_me = a_c;
-    if (lane > c && lane < m) t = fma(-a_c, sm.gsy[pme * M1 + lb_slot<DM>(g, U, c)], t);
+  for (int i = 0; i < m; i++) {  // newest to oldest
+    const double2 s = sm.lbs[k * NP + lk], y = sm.lby[k * NP + lk];
+    const double a = sm.rho[k] * wsum(act ? pdot(s.x, s.y, q0, q1) : 0.0);
+    if (lane == i) a_me = a;
+    q0 = fma(-a, y.x, q0); q1 = fma(-a, y.y, q1);
+    k = (k + 1 == M1) ? 0 : k + 1;
   }
-  // w_l = gamma (y_l . q - sum_c a_c (y_l . y_c)); the a_c go through shared memory so the
-  // loads pipeline and only the fma chain is serial
-  if (lane < m) sm.alpha[lane] = a_me;
-  __syncwarp();
-  double wv = yq;
-  if (lane < m) {
-TT_UNROLL_4
-    for (int c = 0; c < m; c++) wv = fma(-sm.alpha[c], sm.gyy[pme * M1 + lb_slot<DM>(g, U, c)], wv);
-  }
-  wv = U.lb_gamma * wv;
-  __syncwarp();
-  // backward recurrence: beta_c = rho_c w_c ; cc_c = a_c - beta_c ; w_l += cc_c (s_c . y_l) for l < c
-  double cc_me = 0.0;
+  q0 = U.lb_gamma * q0; q1 = U.lb_gamma * q1;
 #pragma unroll 1
-  for (int c = m - 1; c >= 0; c--) {
-    const double cc_c = __shfl_sync(FULL, a_me - rho_me * wv, c);
-    if (lane == c) cc_me = cc_c;
-    if (lane < c) wv = fma(cc_c, sm.gsy[lb_slot<DM>(g, U, c) * M1 + pme], wv);
+  for (int i = m - 1; i >= 0; i--) {  // oldest to newest
+    k = (k == 0) ? M1 - 1 : k - 1;
+    const double2 s = sm.lbs[k * NP + lk], y = sm.lby[k * NP + lk];
+    const double beta = sm.rho[k] * wsum(act ? pdot(y.x, y.y, q0, q1) : 0.0);
+    const double cf = __shfl_sync(FULL, a_me, i) - beta;
+    q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
   }
-  if (lane < m) { sm.alpha[lane] = U.lb_gamma * a_me; sm.alpha[M1 + lane] = cc_me; }
-  __syncwarp();
-  // d = gamma q - sum_c (gamma a_c) y_c + sum_c cc_c s_c   (newest-to-oldest, then oldest-to-newest)
-  double q0 = U.lb_gamma * z.d0, q1 = U.lb_gamma * z.d1;
-  if (act) {
-TT_UNROLL_2
-    for (int c = 0; c < m; c++) {
-      const double2 y = sm.lby[lb_slot<DM>(g, U, c) * NP + lane];
-      const double ga = sm.alpha[c];
-      q0 = fma(-ga, y.x, q0); q1 = fma(-ga, y.y, q1);
-    }
-TT_UNROLL_2
-    for (int c = m - 1; c >= 0; c--) {
-      const double2 s = sm.lbs[lb_slot<DM>(g, U, c) * NP + lane];
-      const double cf = sm.alpha[M1 + c];
-      q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
-    }
-  } else {
-    q0 = 0.0; q1 = 0.0;
-  }
-  z.d0 = q0; z.d1 = q1;
+  z.d0 = act ? q0 : 0.0; z.d1 = act ? q1 : 0.0;
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -446,9 +366,9 @@ __device__ __forceinline__ double eval_grad(const DevCfg &g, const WarpSmem &sm,
 // fixed point residual, its norm and <grad, fpr> in one batched reduction
 __device__ __forceinline__ void compute_fpr(Lane &z, Uni &U) {
   z.f0 = z.u0 - z.h0; z.f1 = z.u1 - z.h1;
-  double nf = pdot(z.f0, z.f1, z.f0, z.f1), ip = pdot(z.g0, z.g1, z.f0, z.f1), dm = 0.0;
-  wsum3(nf, ip, dm);
-  U.norm_fpr = sqrt(nf);
+  double nf = pdot(z.f0, z.f1, z.f0, z.f1), ip = pdot(z.g0, z.g1, z.f0, z.f1);
+  wsum2(nf, ip);
+  U.norm_fpr = tt_sqrt(nf);
   U.ip = ip;
 }
 __device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z, const Uni &U,
@@ -614,7 +534,11 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
     }
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
+#ifdef TT_EXPERIMENT_NO_LBFGS  // i-cache experiment only (wrong algorithm: gradient direction)
+      if (false) {
+#else
       if (pass == 0 ? spec : !lbfgs_done) {
+#endif
         PROF_BEGIN(tl)
         {
           PROF_BEGIN(t0)
@@ -644,7 +568,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       if (!got) cost_half = eval_cost<DM, SP>(g, sm, lane, pb, z.h0, z.h1, hc);
       if (spec) {
         const double rhs0 = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
-                            (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
+                            tt_div(GAMMA_L_COEFF, 2.0 * U.gamma) * (U.norm_fpr * U.norm_fpr);
         if (cost_half > rhs0 && U.L < MAX_LIPSCHITZ_CONSTANT) {  // speculation lost
           U.lb_first = s_first; U.lb_head = s_head; U.lb_active = s_active; U.lb_gamma = s_gamma;
           z.os0 = s_os0; z.os1 = s_os1; z.og0 = s_og0; z.og1 = s_og1;
@@ -655,7 +579,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       int it = 0;
       while (true) {
         const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
-                           (GAMMA_L_COEFF / (2.0 * U.gamma)) * (U.norm_fpr * U.norm_fpr);
+                           tt_div(GAMMA_L_COEFF, 2.0 * U.gamma) * (U.norm_fpr * U.norm_fpr);
         if (!(cost_half > rhs && it < MAX_LIPSCHITZ_UPDATE_ITERATIONS &&
               U.L < MAX_LIPSCHITZ_CONSTANT))
           break;
@@ -668,7 +592,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         compute_fpr(z, U);
         it++;
       }
-      U.sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * U.gamma);
+      U.sigma = tt_div(1.0 - GAMMA_L_COEFF, 4.0 * U.gamma);
     }
   }
   if (U.iteration == 0) {
@@ -684,11 +608,10 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       dist2 = U.env_dd; gg = U.env_g2;
     } else {
       const double e0 = z.s0 - z.h0, e1 = z.s1 - z.h1;
-      double dummy = 0.0;
       dist2 = pdot(e0, e1, e0, e1); gg = pdot(z.g0, z.g1, z.g0, z.g1);
-      wsum3(dist2, gg, dummy);
+      wsum2(dist2, gg);
     }
-    const double fbe = U.cost - 0.5 * U.gamma * gg + 0.5 * dist2 / U.gamma;
+    const double fbe = U.cost - 0.5 * U.gamma * gg + tt_div(0.5 * dist2, U.gamma);
     const double rhs_ls = fbe - U.sigma * (U.norm_fpr * U.norm_fpr);
     U.tau = 1.0;
     int nls = 0;
@@ -707,7 +630,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         U.cost = e.psi;
         z.g0 = e.gv; z.g1 = e.gw;
         gradient_and_half_step(g, z, U, p0, p1);
-        const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+        const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + tt_div(0.5 * e.dd, U.gamma);
         U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
         if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
         U.tau /= 2.0;
@@ -731,7 +654,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       if (lane == 0) sm.ctx->n_grad++;
       U.cost = e.psi;
       z.g0 = e.gv; z.g1 = e.gw; z.s0 = e.s0; z.s1 = e.s1; z.h0 = e.h0; z.h1 = e.h1;
-      double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+      double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + tt_div(0.5 * e.dd, U.gamma);
       U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
       U.tau /= 2.0;
@@ -742,7 +665,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         U.cost = e.psi;
         z.g0 = e.gv; z.g1 = e.gw;
         gradient_and_half_step(g, z, U, p0, p1);  // same s = p - gamma g, h = proj(s) the evaluation formed
-        lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + 0.5 * e.dd / U.gamma;
+        lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + tt_div(0.5 * e.dd, U.gamma);
         U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
         if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
         U.tau /= 2.0;
@@ -826,8 +749,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
         const double e0 = t0 - z.g0, e1 = t1 - z.g1;
         double nh = pdot(h0, h1, h0, h1);
         double nd = pdot(e0, e1, e0, e1);
-        double dm = 0.0;
-        wsum3(nh, nd, dm);
+        wsum2(nh, nd);
         U.L = sqrt(nd) / sqrt(nh);
       }
       U.gamma = GAMMA_L_COEFF / fmax(U.L, MIN_L_ESTIMATE);
