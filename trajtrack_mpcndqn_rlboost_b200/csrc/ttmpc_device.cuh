@@ -55,9 +55,9 @@
 // inlined body per use): fewer distinct cache lines at the price of call overhead and less
 // interleaving.  Same operations in the same order either way (bit-identical results); the
 // default is what measured fastest on the B200 (profiles/r2_*).
-//   1 sincos   2 scans   4 divisions / square roots   8 the 4-value reduction of eval_psi
+//   1 sincos   2 scans   4 divisions / square roots   16 literal (UMOV) sincos constants
 #ifndef TT_FACTOR
-#define TT_FACTOR 0
+#define TT_FACTOR 4
 #endif
 namespace ttmpc {
 
@@ -230,16 +230,6 @@ __device__ __forceinline__ double wsum_inl(double v) {
   return v;
 }
 static __device__ __noinline__ double wsum(double v) { return wsum_inl(v); }
-// all-reduce of two values: 7 double shuffles instead of 10
-__device__ __forceinline__ void wsum2_inl(double &a, double &b, int lane) {
-  const bool b4 = (lane & 16) != 0;
-  double x = b4 ? b : a;
-  const double sx = b4 ? a : b;
-  x += __shfl_xor_sync(FULL, sx, 16);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-  a = __shfl_sync(FULL, x, 0); b = __shfl_sync(FULL, x, 16);
-}
 // all-reduce of four values: 10 double shuffles instead of 20
 __device__ __forceinline__ void wsum4_inl(double &a, double &b, double &c, double &d, int lane) {
   const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
@@ -254,20 +244,9 @@ __device__ __forceinline__ void wsum4_inl(double &a, double &b, double &c, doubl
   a = __shfl_sync(FULL, z, 0); b = __shfl_sync(FULL, z, 8);
   c = __shfl_sync(FULL, z, 16); d = __shfl_sync(FULL, z, 24);
 }
-struct D3 { double a, b, c; };
 struct D4 { double a, b, c, d; };
-static __device__ __noinline__ D2 wsum2v(double a, double b) {
-  wsum2_inl(a, b, threadIdx.x & 31);
-  D2 r; r.a = a; r.b = b;
-  return r;
-}
-static __device__ __noinline__ D3 wsum3v(double a, double b, double c) {
-  double d = 0.0;
-  wsum4_inl(a, b, c, d, threadIdx.x & 31);
-  D3 r; r.a = a; r.b = b; r.c = c;
-  return r;
-}
-#if TT_FACTOR & 8
+// ONE out-of-line copy serves every 2-, 3- and 4-value all-reduce of the solve (unused slots carry
+// zeros; each value goes through its own butterfly tree, so the zeros change nothing)
 static __device__ __noinline__ D4 wsum4v(double a, double b, double c, double d) {
   wsum4_inl(a, b, c, d, threadIdx.x & 31);
   D4 r; r.a = a; r.b = b; r.c = c; r.d = d;
@@ -277,15 +256,12 @@ __device__ __forceinline__ void wsum4(double &a, double &b, double &c, double &d
   const D4 r = wsum4v(a, b, c, d);
   a = r.a; b = r.b; c = r.c; d = r.d;
 }
-#else
-__device__ __forceinline__ void wsum4(double &a, double &b, double &c, double &d, int lane) { wsum4_inl(a, b, c, d, lane); }
-#endif
 __device__ __forceinline__ void wsum2(double &a, double &b) {
-  const D2 r = wsum2v(a, b);
+  const D4 r = wsum4v(a, b, 0.0, 0.0);
   a = r.a; b = r.b;
 }
 __device__ __forceinline__ void wsum3(double &a, double &b, double &c) {
-  const D3 r = wsum3v(a, b, c);
+  const D4 r = wsum4v(a, b, c, 0.0);
   a = r.a; b = r.b; c = r.c;
 }
 __device__ __forceinline__ double clipd_ref(double z, double lo, double hi) {
@@ -761,11 +737,18 @@ TT_UNROLL_2
   // ---- fleet collision (l.207-211): contacts are rare -> fp32 prefilter from shared memory,
   //      one vote, then the exact fp64 terms (parameters in global memory) for the flagged
   //      robots in the same order (Nother <= 32)
+  //      Both obstacle blocks sit behind ONE warp-uniform test: a scene whose box meets no other
+  //      robot and no moving obstacle (every scene of the static workload) walks around ~2 KB of code.
+  const unsigned fleet_todo = in_box ? cx->fleet_live : (Nother >= 32 ? 0xffffffffu : ((1u << Nother) - 1u));
+  const unsigned long long dyn_todo = in_box ? cx->dyn_live : (Ndyn >= 64 ? ~0ull : ((1ull << Ndyn) - 1ull));
+  unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
+  bool any_hard = false;
+  if (fleet_todo != 0u || dyn_todo != 0ull) {
   const float Xf = (float)X, Yf = (float)Y;
   {
     unsigned hit = 0;
     const float thr = cx->fleet_thr;
-    unsigned todo = in_box ? cx->fleet_live : (Nother >= 32 ? 0xffffffffu : ((1u << Nother) - 1u));
+    unsigned todo = fleet_todo;
     while (todo) {
       const int j = __ffs(todo) - 1;
       todo &= todo - 1;
@@ -794,10 +777,9 @@ TT_UNROLL_2
   // ---- dynamic obstacles (l.225-237): hard penalty D_j and soft cost.
   //      fp32 bounding test from shared memory first; the exact fp64 body (global
   //      table) only runs for pairs that can be non-zero.
-  unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
   {
     unsigned long long near_mask = 0;
-    unsigned long long todo = in_box ? cx->dyn_live : (Ndyn >= 64 ? ~0ull : ((1ull << Ndyn) - 1ull));
+    unsigned long long todo = dyn_todo;
     while (todo) {
       const int j = __ffsll((long long)todo) - 1;
       todo &= todo - 1;
@@ -845,7 +827,7 @@ TT_UNROLL_2
     }
   }
   // hard terms are rare: one vote for the whole loop, per-obstacle sums only when needed
-  const bool any_hard = __any_sync(FULL, hard_mask != 0);
+  any_hard = __any_sync(FULL, hard_mask != 0);
   if (__builtin_expect(any_hard, 0)) {
     const unsigned lo = __reduce_or_sync(FULL, (unsigned)hard_mask);
     const unsigned hi = __reduce_or_sync(FULL, (unsigned)(hard_mask >> 32));
@@ -869,6 +851,7 @@ TT_UNROLL_2
     }
     __syncwarp();
   }
+  }  // fleet_todo | dyn_todo
   EPROF(3)
   // ---- terminal cost (l.242)
   double gt = 0.0;
@@ -881,50 +864,38 @@ TT_UNROLL_2
       gt = 2.0 * cx->qthetaN * dtg;
     }
   }
-  // ---- static obstacles (l.214-220): hard penalty only.  Being inside a polygon is rare:
-  //      flag, one vote, second pass over the flagged obstacles in the same order.
+  // ---- static obstacles (l.214-220): hard penalty only.  One pass: the edge products of an
+  //      obstacle are formed once; its sum / gradient terms are entered through a warp vote
+  //      (per obstacle) by the lanes that are inside it, in obstacle order like the reference fold.
   {
-    unsigned in_mask = 0;  // Nstcobs <= 32
 TT_UNROLL_4
     for (int i = 0; i < Nstc; i++) {
       const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
+      double m[MAX_EDGE], sq[MAX_EDGE];
       double inside = 1.0;
 #pragma unroll
       for (int e = 0; e < MAX_EDGE; e++) {
         if (e < ne) {
-          const double m = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
-          inside *= m * m;
+          m[e] = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
+          sq[e] = m[e] * m[e];
+          inside *= sq[e];
         }
       }
-      in_mask |= (inside > 0.0 ? 1u : 0u) << i;
-    }
-    if (__builtin_expect(__any_sync(FULL, in_mask != 0), 0)) {
-      while (in_mask) {
-        const int i = __ffs(in_mask) - 1;
-        in_mask &= in_mask - 1;
-        const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
-        double m[MAX_EDGE], sq[MAX_EDGE];
-        double inside = 1.0;
+      if (__builtin_expect(__any_sync(FULL, inside > 0.0), 0)) {
+        if (inside > 0.0) {
+          S_loc += inside;
+          if (GRAD) {
 #pragma unroll
-        for (int e = 0; e < MAX_EDGE; e++) {
-          if (e < ne) {
-            m[e] = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
-            sq[e] = m[e] * m[e];
-            inside *= sq[e];
-          }
-        }
-        S_loc += inside;
-        if (GRAD) {
+            for (int e = 0; e < MAX_EDGE; e++) {
+              if (e < ne) {
+                double rest = 1.0;
 #pragma unroll
-          for (int e = 0; e < MAX_EDGE; e++) {
-            if (e < ne) {
-              double rest = 1.0;
-#pragma unroll
-              for (int e2 = 0; e2 < MAX_EDGE; e2++)
-                if (e2 < ne && e2 != e) rest *= sq[e2];
-              const double coef = rest * (2.0 * m[e]);
-              gSx = fma(coef, na0[e], gSx);
-              gSy = fma(coef, na1[e], gSy);
+                for (int e2 = 0; e2 < MAX_EDGE; e2++)
+                  if (e2 < ne && e2 != e) rest *= sq[e2];
+                const double coef = rest * (2.0 * m[e]);
+                gSx = fma(coef, na0[e], gSx);
+                gSy = fma(coef, na1[e], gSy);
+              }
             }
           }
         }

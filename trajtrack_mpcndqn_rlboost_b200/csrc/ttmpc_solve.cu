@@ -219,9 +219,11 @@ __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity, unsigned l
   return true;
 }
 // SP = split kernel: requests go to the evaluator warp in the peer CTA (always there)
-template <bool SP>
+// HELP = false: the instantiation of panoc_step without any request path (see solve_scene)
+template <bool SP, bool HELP = true>
 __device__ __forceinline__ bool help_available(const HelpCtl &hc) {
   if constexpr (SP) return hc.enabled;
+  else if constexpr (!HELP) return false;
   else return hc.enabled && *hc.slot >= 0;
 }
 template <bool SP>
@@ -501,7 +503,7 @@ __device__ bool help_long_running_mate(const DevCfg &g, const SolveArgs &A, CtaH
 }
 
 // PANOCEngine::step.  Returns true to continue.
-template <class DM, bool SP>
+template <class DM, bool SP, bool HELP>
 __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, int lane, const Problem &pb,
                            Lane &z, Uni &U, double tolerance, HelpCtl &hc) {
   PROF_BEGIN(t_step)
@@ -522,7 +524,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
   bool lbfgs_done = false;
   {
     double cost_half = 0.0;
-    const bool spec = __builtin_expect(help_available<SP>(hc), SP ? 1 : 0);
+    const bool spec = __builtin_expect(help_available<SP, HELP>(hc), SP ? 1 : 0);
     int s_first = 0, s_head = 0, s_active = 0;
     double s_gamma = 0.0, s_os0 = 0.0, s_os1 = 0.0, s_og0 = 0.0, s_og1 = 0.0;
     if (spec) {
@@ -639,7 +641,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       // with a helper: the next candidate (tau/2) is evaluated speculatively at the same time
       bool posted = false;
       double n0 = 0.0, n1 = 0.0;
-      if (__builtin_expect(nls < MAX_LINESEARCH_ITERATIONS && help_available<SP>(hc), 0)) {
+      if (__builtin_expect(nls < MAX_LINESEARCH_ITERATIONS && help_available<SP, HELP>(hc), 0)) {
         const double tau2 = U.tau / 2.0, one_m2 = 1.0 - tau2;
         n0 = fma(-tau2, z.d0, fma(-one_m2, z.f0, z.u0));
         n1 = fma(-tau2, z.d1, fma(-one_m2, z.f1, z.u1));
@@ -760,7 +762,20 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
       int num_iter = 0;
       bool cont = true;
       while (true) {
-        const bool flag = panoc_step<DM, SP>(g, sm, lane, pb, z, U, g.tol, hc);
+        // Two instantiations of the step: the plain one (no request path at all) runs while no
+        // helper is attached to this warp -- every iteration of a bulk batch -- and keeps the hot
+        // loop ~2 KB shorter (it is bound by the instruction cache); the
+        // helper-aware one takes over the moment a helper attaches (tail of a batch, one scene
+        // alone).  Same arithmetic: results do not depend on which one ran.
+        bool flag;
+        if constexpr (SP) {
+          flag = panoc_step<DM, true, true>(g, sm, lane, pb, z, U, g.tol, hc);
+        } else {
+          if (__builtin_expect(hc.enabled && *hc.slot >= 0, 0))
+            flag = panoc_step<DM, false, true>(g, sm, lane, pb, z, U, g.tol, hc);
+          else
+            flag = panoc_step<DM, false, false>(g, sm, lane, pb, z, U, g.tol, hc);
+        }
         if (!(flag && cont)) break;
         num_iter++;
         cont = num_iter < g.max_inner;
