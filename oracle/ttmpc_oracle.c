@@ -529,7 +529,14 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
     double thb = fma(0.5, tw[k], tha), thc = tha + tw[k];
     tt_sincos(tha, &sa[k], &ca[k]);
     tt_sincos(thb, &sb[k], &cb[k]);
-    tt_sincos(thc, &sc[k], &cc[k]);
+    tt_sincos(thc, &sc[k], &cc[k]); /* N == 32 only, see below */
+  }
+  /* end-of-step heading = start heading of the next step: for N < 32 the kernel takes sin / cos
+     of theta_k + ts w_k from lane k + 1 (whose start heading is th0 + scan_k) instead of a third
+     sincos (lane 31 reads itself; it is beyond the horizon and multiplied by v = 0) */
+  if (N < WL)
+    for (int k = 0; k < WL; k++) { sc[k] = sa[k + 1 < WL ? k + 1 : k]; cc[k] = ca[k + 1 < WL ? k + 1 : k]; }
+  for (int k = 0; k < WL; k++) {
     Cs[k] = fma(4.0, cb[k], ca[k]) + cc[k];
     Ss[k] = fma(4.0, sb[k], sa[k]) + sc[k];
     hv[k] = h6 * v[k];

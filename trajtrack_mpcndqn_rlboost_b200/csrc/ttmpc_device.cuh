@@ -65,6 +65,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_MEM = 16;
 constexpr int MAX_EDGE = 8;
 constexpr int DYN_FIELDS = 10;  // per (obstacle, step): see stage_scene
+constexpr int DYN_SLOTS = 4;    // live dynamic obstacles whose table rows are kept in shared memory
 
 struct DevCfg {
   int N, Nother, Nstc, ne, nstcobs, Ndyn, mem, max_inner, max_outer;
@@ -330,6 +331,7 @@ struct WarpSmem {
   double *vref;   // [N] speed reference
   float2 *fleet;  // [Nother][N] other robots' (x, y), fp32 copy for the contact prefilter
   float *dynb;    // [Ndyn][N][3] conservative fp32 bounding test: cx cy R2
+  double *dynt;   // [DYN_SLOTS][DYN_FIELDS][N] table rows of the first live dynamic obstacles
   double2 *lbs;   // [(mem+1)][NP]  L-BFGS s rows; NP = N|1 (odd stride: rows read by
   double2 *lby;   // [(mem+1)][NP]  different lanes fall in different banks)
   double *rho;    // [mem+1]
@@ -352,8 +354,18 @@ struct HelpHdr {
 
 // Compile-time problem dimensions (0 = take the value from DevCfg at run time).
 // The default configuration (config/mpc_default.yaml) gets a fully specialised kernel.
+__device__ __forceinline__ int first_bit(unsigned m) { return __ffs((int)m) - 1; }
+__device__ __forceinline__ int first_bit(unsigned long long m) { return __ffsll((long long)m) - 1; }
+__device__ __forceinline__ int pop_bits(unsigned m) { return __popc(m); }
+__device__ __forceinline__ int pop_bits(unsigned long long m) { return __popcll(m); }
+template <bool WIDE> struct DynMask { using type = unsigned long long; };
+template <> struct DynMask<false> { using type = unsigned; };
+
 template <int N_, int NO_, int NS_, int NE_, int ND_, int MEM_ = 0>
 struct Dims {
+  // bit mask over the dynamic obstacles: 32 bits when the compile-time count allows (64-bit
+  // find-first-set / shifts are ~10 instructions each on sm_100)
+  using dmask = typename DynMask<(N_ == 0 || ND_ > 32)>::type;
   __device__ __forceinline__ static int mem(const DevCfg &g) { return N_ ? MEM_ : g.mem; }
   __device__ __forceinline__ static int N(const DevCfg &g) { return N_ ? N_ : g.N; }
   __device__ __forceinline__ static int Nother(const DevCfg &g) { return N_ ? NO_ : g.Nother; }
@@ -374,6 +386,7 @@ __host__ __device__ inline int smem_bytes_per_warp(int N, int Nother, int Nstc, 
   b += sizeof(double) * ((N + 1) / 2 * 2);
   b += (sizeof(float2) * (size_t)Nother * N + 15) / 16 * 16;
   b += (sizeof(float) * 3 * (size_t)Ndyn * N + 15) / 16 * 16;
+  b += sizeof(double) * (size_t)(Ndyn ? DYN_SLOTS * DYN_FIELDS * N : 0);
   const int NP = N | 1;
   b += sizeof(double2) * (size_t)(mem + 1) * NP * 2;
   b += sizeof(double) * ((mem + 2) / 2 * 2);
@@ -396,6 +409,7 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
   w.lby = reinterpret_cast<double2 *>(q); q += sizeof(double2) * (size_t)(MEM + 1) * NP;
   w.fleet = reinterpret_cast<float2 *>(q); q += (sizeof(float2) * (size_t)Nother * N + 15) / 16 * 16;
   w.dynb = reinterpret_cast<float *>(q); q += (sizeof(float) * 3 * (size_t)Ndyn * N + 15) / 16 * 16;
+  w.dynt = reinterpret_cast<double *>(q); q += sizeof(double) * (size_t)(Ndyn ? DYN_SLOTS * DYN_FIELDS * N : 0);
   w.seg = reinterpret_cast<double *>(q); q += sizeof(double) * 6 * N;
   w.os = reinterpret_cast<double *>(q); q += sizeof(double) * ((Nstc * nstcobs + 1) / 2 * 2);
   w.D = reinterpret_cast<double *>(q); q += sizeof(double) * ((Ndyn + 1) / 2 * 2);
@@ -416,6 +430,20 @@ __device__ __forceinline__ WarpSmem carve(unsigned char *base, const DevCfg &g) 
 //   5 1/(rx+1e-6)^2  6 1/(ry+1e-6)^2  7 1/(rx+m+1e-6)^2  8 1/(ry+m+1e-6)^2  9 alpha*qdyn[k]
 __device__ __forceinline__ double &dynf(double *t, const DevCfg &g, int f, int j, int k) {
   return t[((size_t)f * g.Ndyn + j) * g.N + k];
+}
+
+// Row of obstacle j's table for this lane's column: shared memory for the first DYN_SLOTS live
+// obstacles, the warp's global scratch otherwise.  field f of the row = p[f * sf].
+struct DynRow { const double *p; int sf; };
+template <class M>
+__device__ __forceinline__ DynRow dyn_row(const WarpSmem &sm, const WarpCtx *cx, int j, int N, int Ndyn, int lk) {
+  const M live = (M)cx->dyn_live;
+  const int slot = pop_bits((M)(live & (((M)1 << j) - (M)1)));
+  const bool in_s = (live >> j & (M)1) != (M)0 && slot < DYN_SLOTS;
+  DynRow r;
+  r.p = in_s ? sm.dynt + (size_t)slot * DYN_FIELDS * N + lk : cx->dyn + (size_t)j * N + lk;
+  r.sf = in_s ? N : Ndyn * N;
+  return r;
 }
 
 // Staging, part 1: everything before the dynamic-obstacle block.  `p` points at a copy of the
@@ -521,37 +549,8 @@ __device__ inline void stage_part2(const DevCfg &g, const WarpSmem &sm, const do
                                    double *dyn_scratch, int lane) {
   WarpCtx *c = sm.ctx;
   const int npair = g.Ndyn * g.N;
-  for (int t = lane; t < npair; t += 32) {
-    int j = t / g.N, k = t - j * g.N;
-    const double *e = od + (size_t)t * 6;  // obstacle-major, then step: contiguous records
-    double cx = e[0], cy = e[1], rx = e[2], ry = e[3], ang = e[4], alpha = e[5];
-    double sa, ca;
-    tt_sincos(ang, &sa, &ca);
-    double Rx = rx + 1e-6, Ry = ry + 1e-6;
-    double Rxm = rx + g.margin + 1e-6, Rym = ry + g.margin + 1e-6;
-    double rmax = fmax(fmax(fabs(Rx), fabs(Ry)), fmax(fabs(Rxm), fabs(Rym)));
-    dynf(dyn_scratch, g, 0, j, k) = cx;
-    dynf(dyn_scratch, g, 1, j, k) = cy;
-    dynf(dyn_scratch, g, 2, j, k) = rmax * rmax * (1.0 + 1e-9);
-    dynf(dyn_scratch, g, 3, j, k) = ca;
-    dynf(dyn_scratch, g, 4, j, k) = sa;
-    dynf(dyn_scratch, g, 5, j, k) = 1.0 / (Rx * Rx);
-    dynf(dyn_scratch, g, 6, j, k) = 1.0 / (Ry * Ry);
-    dynf(dyn_scratch, g, 7, j, k) = 1.0 / (Rxm * Rxm);
-    dynf(dyn_scratch, g, 8, j, k) = 1.0 / (Rym * Rym);
-    dynf(dyn_scratch, g, 9, j, k) = alpha * qdyn[k];
-    // conservative fp32 copy of the bounding test: the radius is padded by the worst
-    // rounding of the fp32 centre / position (8 ulp_f32 of the coordinates) so a pair the
-    // exact fp64 test accepts is never rejected here; rejected pairs contribute exactly 0
-    {
-      const double pad = 4.8e-7 * (fabs(cx) + fabs(cy) + 2.0 * rmax + 1.0) + 1e-6;
-      const double rp = rmax + pad;
-      float r2f = __double2float_ru(rp * rp * (1.0 + 1e-6));
-      if (!(rmax == rmax) || !(cx == cx) || !(cy == cy)) r2f = 0.0f;  // NaN input: exact test is false too
-      sm.dynb[3 * t] = (float)cx; sm.dynb[3 * t + 1] = (float)cy; sm.dynb[3 * t + 2] = r2f;
-    }
-  }
   // live mask of the box-guarded compaction, dynamic obstacles (NaN / inf coordinates stay live)
+  unsigned long long live;
   {
     const double x0 = c->x0, y0 = c->y0;
     const double bh = c->box_half;
@@ -565,7 +564,43 @@ __device__ inline void stage_part2(const DevCfg &g, const WarpSmem &sm, const do
       if (!outside) dl |= 1ull << j;
     }
     const unsigned dlo = __reduce_or_sync(FULL, (unsigned)dl), dhi = __reduce_or_sync(FULL, (unsigned)(dl >> 32));
-    if (lane == 0) c->dyn_live = ((unsigned long long)dhi << 32) | dlo;
+    live = ((unsigned long long)dhi << 32) | dlo;
+    if (lane == 0) c->dyn_live = live;
+  }
+  for (int t = lane; t < npair; t += 32) {
+    int j = t / g.N, k = t - j * g.N;
+    const double *e = od + (size_t)t * 6;  // obstacle-major, then step: contiguous records
+    double cx = e[0], cy = e[1], rx = e[2], ry = e[3], ang = e[4], alpha = e[5];
+    double sa, ca;
+    tt_sincos(ang, &sa, &ca);
+    double Rx = rx + 1e-6, Ry = ry + 1e-6;
+    double Rxm = rx + g.margin + 1e-6, Rym = ry + g.margin + 1e-6;
+    double rmax = fmax(fmax(fabs(Rx), fabs(Ry)), fmax(fabs(Rxm), fabs(Rym)));
+    double f[DYN_FIELDS];
+    f[0] = cx; f[1] = cy; f[2] = rmax * rmax * (1.0 + 1e-9); f[3] = ca; f[4] = sa;
+    f[5] = 1.0 / (Rx * Rx); f[6] = 1.0 / (Ry * Ry); f[7] = 1.0 / (Rxm * Rxm); f[8] = 1.0 / (Rym * Rym);
+    f[9] = alpha * qdyn[k];
+#pragma unroll
+    for (int q = 0; q < DYN_FIELDS; q++) dynf(dyn_scratch, g, q, j, k) = f[q];
+    // the first DYN_SLOTS live obstacles also get their rows in shared memory (eval_psi reads them
+    // there: the obstacles a scene actually meets are few, their rows are read in every evaluation)
+    {
+      const int slot = __popcll(live & ((1ull << j) - 1ull));
+      if ((live >> j & 1ull) && slot < DYN_SLOTS) {
+#pragma unroll
+        for (int q = 0; q < DYN_FIELDS; q++) sm.dynt[((size_t)slot * DYN_FIELDS + q) * g.N + k] = f[q];
+      }
+    }
+    // conservative fp32 copy of the bounding test: the radius is padded by the worst
+    // rounding of the fp32 centre / position (8 ulp_f32 of the coordinates) so a pair the
+    // exact fp64 test accepts is never rejected here; rejected pairs contribute exactly 0
+    {
+      const double pad = 4.8e-7 * (fabs(cx) + fabs(cy) + 2.0 * rmax + 1.0) + 1e-6;
+      const double rp = rmax + pad;
+      float r2f = __double2float_ru(rp * rp * (1.0 + 1e-6));
+      if (!(rmax == rmax) || !(cx == cx) || !(cy == cy)) r2f = 0.0f;  // NaN input: exact test is false too
+      sm.dynb[3 * t] = (float)cx; sm.dynb[3 * t + 1] = (float)cy; sm.dynb[3 * t + 2] = r2f;
+    }
   }
   __syncwarp();
 }
@@ -653,7 +688,15 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   double sa, ca, sb, cb, sc, cc;
   tt_sincos_hot(tha, &sa, &ca);
   tt_sincos_hot(thb, &sb, &cb);
-  tt_sincos_hot(thc, &sc, &cc);
+  // heading at the end of step k = heading at the start of step k + 1 (lane k + 1 holds its sine
+  // and cosine; lane N exists and carries w = 0 when N < 32): two sincos per evaluation, not three.
+  // The two values differ by the rounding of (th0 + scan_{k-1}) + ts w_k against th0 + scan_k;
+  // the oracle's WARP order does the same.
+  if (N < 32) {
+    sc = __shfl_down_sync(FULL, sa, 1); cc = __shfl_down_sync(FULL, ca, 1);
+  } else {
+    tt_sincos_hot(thc, &sc, &cc);
+  }
   const double Cs = fma(4.0, cb, ca) + cc, Ss = fma(4.0, sb, sa) + sc;
   const double hv = g.h6 * v;
   const double dx = hv * Cs, dy = hv * Ss;
@@ -740,8 +783,10 @@ TT_UNROLL_2
   //      Both obstacle blocks sit behind ONE warp-uniform test: a scene whose box meets no other
   //      robot and no moving obstacle (every scene of the static workload) walks around ~2 KB of code.
   const unsigned fleet_todo = in_box ? cx->fleet_live : (Nother >= 32 ? 0xffffffffu : ((1u << Nother) - 1u));
-  const unsigned long long dyn_todo = in_box ? cx->dyn_live : (Ndyn >= 64 ? ~0ull : ((1ull << Ndyn) - 1ull));
-  unsigned long long hard_mask = 0;  // obstacles with a positive hard term on this lane
+  using dmask = typename DM::dmask;
+  const dmask dyn_todo = in_box ? (dmask)cx->dyn_live
+                                : (Ndyn >= (int)(8 * sizeof(dmask)) ? ~(dmask)0 : (((dmask)1 << Ndyn) - (dmask)1));
+  dmask hard_mask = 0;  // obstacles with a positive hard term on this lane
   bool any_hard = false;
   if (fleet_todo != 0u || dyn_todo != 0ull) {
   const float Xf = (float)X, Yf = (float)Y;
@@ -778,38 +823,37 @@ TT_UNROLL_2
   //      fp32 bounding test from shared memory first; the exact fp64 body (global
   //      table) only runs for pairs that can be non-zero.
   {
-    unsigned long long near_mask = 0;
-    unsigned long long todo = dyn_todo;
+    dmask near_mask = 0;
+    dmask todo = dyn_todo;
     while (todo) {
-      const int j = __ffsll((long long)todo) - 1;
+      const int j = first_bit(todo);
       todo &= todo - 1;
       const float *b = sm.dynb + 3 * (j * N + lk);
       const float exf = Xf - b[0], eyf = Yf - b[1];
-      near_mask |= (unsigned long long)((exf * exf + eyf * eyf) < b[2] ? 1u : 0u) << j;
+      near_mask |= (dmask)((exf * exf + eyf * eyf) < b[2] ? 1u : 0u) << j;
     }
     if (__builtin_expect(__any_sync(FULL, near_mask != 0), 0)) {
-      const double *T = cx->dyn;
       double soft = 0.0;
       int bodies = 0;
       while (near_mask) {
-        const int j = __ffsll((long long)near_mask) - 1;
+        const int j = first_bit(near_mask);
         near_mask &= near_mask - 1;
-        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
-        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lk];
-        if (fma(ey, ey, ex * ex) < T[((size_t)2 * Ndyn + j) * N + lk]) {
+        const DynRow T = dyn_row<dmask>(sm, cx, j, N, Ndyn, lk);
+        const double ex = X - T.p[0];
+        const double ey = Y - T.p[T.sf];
+        if (fma(ey, ey, ex * ex) < T.p[2 * T.sf]) {
           bodies++;
-          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lk];
-          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lk];
+          const double ca_ = T.p[3 * T.sf];
+          const double sa_ = T.p[4 * T.sf];
           const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
           const double A2 = A * A, B2 = B * B;
-          const double in1 = fma(-B2, T[((size_t)6 * Ndyn + j) * N + lk],
-                                 fma(-A2, T[((size_t)5 * Ndyn + j) * N + lk], 1.0));
-          if (in1 > 0.0) hard_mask |= 1ull << j;
-          const double iRxm = T[((size_t)7 * Ndyn + j) * N + lk];
-          const double iRym = T[((size_t)8 * Ndyn + j) * N + lk];
+          const double in1 = fma(-B2, T.p[6 * T.sf], fma(-A2, T.p[5 * T.sf], 1.0));
+          if (in1 > 0.0) hard_mask |= (dmask)1 << j;
+          const double iRxm = T.p[7 * T.sf];
+          const double iRym = T.p[8 * T.sf];
           const double in2 = fma(-B2, iRym, fma(-A2, iRxm, 1.0));
           if (in2 > 0.0) {
-            const double ws = T[((size_t)9 * Ndyn + j) * N + lk];
+            const double ws = T.p[9 * T.sf];
             soft = fma(in2 * in2, ws, soft);
             if (GRAD) {
               const double wg = ws * (2.0 * in2);
@@ -829,22 +873,29 @@ TT_UNROLL_2
   // hard terms are rare: one vote for the whole loop, per-obstacle sums only when needed
   any_hard = __any_sync(FULL, hard_mask != 0);
   if (__builtin_expect(any_hard, 0)) {
-    const unsigned lo = __reduce_or_sync(FULL, (unsigned)hard_mask);
-    const unsigned hi = __reduce_or_sync(FULL, (unsigned)(hard_mask >> 32));
-    const unsigned long long warp_hard = ((unsigned long long)hi << 32) | lo;
-    const double *T = cx->dyn;
-#pragma unroll 1
-    for (int j = 0; j < Ndyn; j++) {
-      if (!(warp_hard >> j & 1ull)) { if (lane == 0) Dv[j] = 0.0; continue; }
+    dmask warp_hard;
+    if constexpr (sizeof(dmask) == 4) {
+      warp_hard = __reduce_or_sync(FULL, (unsigned)hard_mask);
+    } else {
+      const unsigned lo = __reduce_or_sync(FULL, (unsigned)hard_mask);
+      const unsigned hi = __reduce_or_sync(FULL, (unsigned)((unsigned long long)hard_mask >> 32));
+      warp_hard = (dmask)(((unsigned long long)hi << 32) | lo);
+    }
+    for (int j = lane; j < Ndyn; j += 32) Dv[j] = 0.0;
+    __syncwarp();
+    // per-obstacle sums only for the obstacles some lane is inside of
+    while (warp_hard) {
+      const int j = first_bit(warp_hard);
+      warp_hard &= warp_hard - 1;
       double in1 = 0.0;
-      if (hard_mask >> j & 1ull) {
-        const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
-        const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lk];
-        const double ca_ = T[((size_t)3 * Ndyn + j) * N + lk];
-        const double sa_ = T[((size_t)4 * Ndyn + j) * N + lk];
+      if (hard_mask >> j & (dmask)1) {
+        const DynRow T = dyn_row<dmask>(sm, cx, j, N, Ndyn, lk);
+        const double ex = X - T.p[0];
+        const double ey = Y - T.p[T.sf];
+        const double ca_ = T.p[3 * T.sf];
+        const double sa_ = T.p[4 * T.sf];
         const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
-        in1 = fma(-(B * B), T[((size_t)6 * Ndyn + j) * N + lk],
-                  fma(-(A * A), T[((size_t)5 * Ndyn + j) * N + lk], 1.0));
+        in1 = fma(-(B * B), T.p[6 * T.sf], fma(-(A * A), T.p[5 * T.sf], 1.0));
       }
       const double Dj = wsum(in1);
       if (lane == 0) Dv[j] = Dj;
@@ -955,17 +1006,17 @@ TT_UNROLL_4
       gx = fma(cs_, gSx, gx);
       gy = fma(cs_, gSy, gy);
       if (__builtin_expect(any_hard, 0)) {
-        unsigned long long mk = hard_mask;
-        const double *T = cx->dyn;
+        dmask mk = hard_mask;
         while (mk) {
-          const int j = __ffsll((long long)mk) - 1;
+          const int j = first_bit(mk);
           mk &= mk - 1;
-          const double ex = X - T[((size_t)0 * Ndyn + j) * N + lk];
-          const double ey = Y - T[((size_t)1 * Ndyn + j) * N + lk];
-          const double ca_ = T[((size_t)3 * Ndyn + j) * N + lk];
-          const double sa_ = T[((size_t)4 * Ndyn + j) * N + lk];
-          const double iRx = T[((size_t)5 * Ndyn + j) * N + lk];
-          const double iRy = T[((size_t)6 * Ndyn + j) * N + lk];
+          const DynRow T = dyn_row<dmask>(sm, cx, j, N, Ndyn, lk);
+          const double ex = X - T.p[0];
+          const double ey = Y - T.p[T.sf];
+          const double ca_ = T.p[3 * T.sf];
+          const double sa_ = T.p[4 * T.sf];
+          const double iRx = T.p[5 * T.sf];
+          const double iRy = T.p[6 * T.sf];
           const double A = fma(ey, sa_, ex * ca_), B = fma(-ey, ca_, ex * sa_);
           const double wg = c * (S + Dv[j]);
           const double tA = A * iRx, tB = B * iRy;
