@@ -97,7 +97,13 @@ typedef struct ttmpc_config {
   int lbfgs_memory;              /* 10, max 16                           */
   int max_inner_iterations;      /* 500                                  */
   int max_outer_iterations;      /* 10                                   */
-  int _pad1;
+  int max_duration_ms;           /* wall-clock budget of ONE scene's solve, 5000 =
+                                    MAX_SOVLER_TIME (mpc_generator.py:22,270: with_max_duration_micros);
+                                    0 = no limit.  Measured on the device from the moment the scene's
+                                    solve starts; checked where OpEn checks it (after every PANOC step,
+                                    before every outer iteration) -> TTMPC_NOT_CONVERGED_OUT_OF_TIME.
+                                    Like in the reference, a solve that hits the budget is not
+                                    reproducible; the CPU oracle ignores the field.               */
 } ttmpc_config;
 
 /* Fill cfg with config/mpc_default.yaml + opengen defaults. */
@@ -209,6 +215,9 @@ typedef struct ttdqn_qnet {
 } ttdqn_qnet;
 
 void ttdqn_default_layout(ttdqn_scene_layout *lay);
+/* Last failure of a ttdqn_* entry point on the calling thread (the same text is also what
+ * ttmpc_last_error() returns, so one query serves the whole library).                     */
+const char *ttdqn_last_error(void);
 
 /* Device-resident batched observe + act.
  *   d_agent    [n][3]   x y theta (fp64)

@@ -41,12 +41,15 @@ def test_pack_bit_exact():
 def test_closed_loop_bit_exact():
     n, steps = 24, 4
     fp, fh = _make(n, seed=9, max_inner_iterations=60, max_outer_iterations=4)
+    y = None  # the multipliers persist from step to step, like in the reference's Solver objects
     for k in range(steps):
         fp.step()
         fp.torch.cuda.synchronize()
         p = O.fleet_pack(fh, use_libm=False)
         assert np.array_equal(fp.p.cpu().numpy(), p), f"packed parameters differ at step {k}"
-        ref = O.solve_batch(fp.cfg, p, threads=8, warp=True)
+        ref = O.solve_batch(fp.cfg, p, y0=y, threads=8, warp=True)
+        y = ref["y"]
+        assert np.array_equal(fp.y.cpu().numpy(), y), f"multipliers differ at step {k}"
         assert np.array_equal(fp.u.cpu().numpy(), ref["u"]), f"controls differ at step {k}"
         assert np.array_equal(fp.exit_status.cpu().numpy(), ref["exit_status"])
         O.fleet_advance(fh, ref["u"], ref["exit_status"], use_libm=False)
@@ -133,6 +136,7 @@ def test_hint_switch_on_device_matches_oracle():
     fh.use_hint = np.zeros(n, np.int32)
     g = torch.Generator(device="cpu").manual_seed(0)
     seen_on = 0
+    y = None  # multipliers carry over from step to step (FleetPlanner.step default)
     for k in range(4):
         agent5 = torch.cat([fp.state, fp.last_u], 1).contiguous()
         act = torch.randint(0, 9, (n,), generator=g, dtype=torch.int32).cuda()
@@ -144,8 +148,35 @@ def test_hint_switch_on_device_matches_oracle():
         assert np.array_equal(fp.use_hint.cpu().numpy(), fh.use_hint), f"switch decision differs at step {k}"
         assert np.array_equal(fp.sw_state.cpu().numpy(), fh.sw_state)
         assert np.array_equal(fp.p.cpu().numpy(), p)
-        ref = O.solve_batch(fp.cfg, p, threads=8, warp=True)
+        ref = O.solve_batch(fp.cfg, p, y0=y, threads=8, warp=True)
+        y = ref["y"]
         O.fleet_advance(fh, ref["u"], ref["exit_status"], use_libm=False)
         assert np.array_equal(fp.state.cpu().numpy(), fh.state)
         seen_on += int(fh.use_hint.sum())
     assert seen_on > 0
+
+
+def test_fleet_keeps_multipliers_like_per_robot_solver_objects():
+    """FleetPlanner.step() must do what a loop of per-robot Solver objects does -- each
+    robot's multipliers carry over from one control step to the next (the PyO3 Solver owns its
+    AlmCache).  Six robots, four steps: the fleet's controls equal, bit for bit, those of six
+    `Solver` mirrors fed the same packed vectors; a fleet stepped with keep_multipliers=False
+    (fresh solver every step) differs from step 2 on for at least one robot."""
+    n, steps = 6, 4
+    fp, _ = _make(n, seed=31, max_inner_iterations=80, max_outer_iterations=5)
+    cold, _ = _make(n, seed=31, max_inner_iterations=80, max_outer_iterations=5)
+    solvers = [t.Solver(fp.cfg) for _ in range(n)]
+    differs = False
+    for k in range(steps):
+        fp.pack(); fp.torch.cuda.synchronize()
+        p = fp.p.cpu().numpy().copy()
+        fp.step(); fp.torch.cuda.synchronize()
+        u = fp.u.cpu().numpy()
+        for i, sv in enumerate(solvers):
+            sol = sv.run(p[i])
+            assert sol is not None
+            assert np.array_equal(np.asarray(sol.solution), u[i]), f"robot {i} differs at step {k}"
+        cold.step(keep_multipliers=False); cold.torch.cuda.synchronize()
+        if k >= 1 and not np.array_equal(cold.u.cpu().numpy(), u):
+            differs = True
+    assert differs, "keeping the multipliers made no difference: the test scenes never activate the ALM rows"

@@ -105,6 +105,75 @@ def test_solve_parity_reference_order_easy_scenes(cfg, solver):
     assert np.all(np.abs(sol.cost - ref["cost"])[both] <= 1e-3 * np.maximum(1.0, np.abs(ref["cost"][both])))
 
 
+@pytest.mark.parametrize("name,n", [("static4096", 512), ("mixed4096", 512), ("dynamic8192", 48)])
+def test_gpu_against_reference_order_distribution(name, n):
+    """the GPU against the REFERENCE-order oracle (sequential sums, libm,
+    unfused products like Rust) on every BASELINE workload, with the reference order's 1-ulp
+    self-sensitivity next to it (tools/parity_report.py; numbers in BENCH.md).  north_star's 1e-4 /
+    1e-6 bars are printed, not asserted: the reference-order code does not meet them against itself
+    (tests/test_parity_distribution.py).  Asserted: exit status agreement, the deviation where both
+    converge, and that the GPU sits inside the self-sensitivity envelope -- so a regression shows."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_report as PR
+    rows = PR.run([name], n=n, threads=os.cpu_count() or 1, use_gpu=True, n_dyn=n)
+    k, base = rows[name]["kernel_vs_reference_order"], rows[name]["reference_order_vs_itself_1ulp"]
+    print(PR.markdown(rows))
+    assert rows[name]["kernel_arm"] == "gpu"
+    assert k["status_agree"] >= 0.90
+    assert k["status_agree"] >= base["status_agree"] - 0.08
+    assert k["both_converged"] >= n // 4
+    assert k["conv_du_p50"] <= (5e-3 if name != "dynamic8192" else 3e-2)
+    assert k["du_p50"] <= 10.0 * base["du_p50"] + 1e-3
+    assert k["cost_rel_p50"] <= 10.0 * base["cost_rel_p50"] + 1e-4
+
+
+def test_long_iteration_limits_bit_exact(cfg):
+    """BASELINE configs[2] limits (2000 inner x 20 outer, the dynamic8192 workload) on the GPU,
+    bit for bit against the WARP-order oracle -- scenes that run tens of thousands of PANOC
+    iterations included."""
+    w = t.scenes.WORKLOADS["dynamic8192"]
+    cfg_l = t.Configurator().to_ttmpc(**w["solver"])
+    assert cfg_l.max_inner_iterations == 2000 and cfg_l.max_outer_iterations == 20
+    p = t.scenes.make_scenes(96, cfg_l, seed=77, n_static=w["n_static"], n_dynamic=w["n_dynamic"],
+                             blocking_fraction=w["blocking_fraction"])
+    sol = t.BatchSolver(cfg_l).run(p)
+    ref = O.solve_batch(cfg_l, p, threads=os.cpu_count(), warp=True)
+    assert_parity(sol, ref, 96)
+    assert sol.num_inner_iterations.max() > 2000       # the long limits were actually exercised
+
+
+def test_time_budget_returns_out_of_time(cfg):
+    """max_duration_ms (OpEn's max_duration, MAX_SOVLER_TIME in mpc_generator.py:22): a scene that
+    cannot finish inside the budget comes back as NotConvergedOutOfTime with finite controls; with
+    the budget off (0) or generous the result equals the untimed oracle."""
+    w = t.scenes.WORKLOADS["dynamic8192"]
+    p = t.scenes.make_scenes(64, cfg, seed=5, n_static=3, n_dynamic=4, blocking_fraction=0.5)
+    tight = t.Configurator().to_ttmpc(max_inner_iterations=2000, max_outer_iterations=20, max_duration_ms=1)
+    sol = t.BatchSolver(tight).run(p)
+    assert (sol.exit_status == 2).any(), "no scene ran into the 1 ms budget"
+    assert np.isfinite(sol.solution).all()
+    assert set(np.unique(sol.exit_status)) <= {0, 1, 2}
+    off = t.Configurator().to_ttmpc(max_duration_ms=0)
+    a = t.BatchSolver(off).run(p)
+    b = t.BatchSolver(cfg).run(p)                      # default 5000 ms: never binds here
+    assert np.array_equal(a.solution, b.solution) and np.array_equal(a.exit_status, b.exit_status)
+    assert not (a.exit_status == 2).any()
+
+
+def test_sweep_shapes_use_specialised_kernels_and_match_the_oracle():
+    """BASELINE configs[4]: the horizon / obstacle-count sweep shapes have their own compiled
+    kernels (csrc/ttmpc_solve.cu TTMPC_SOLVE_SHAPES); same bits as the oracle."""
+    for N, nst, ndy in [(10, 10, 15), (32, 10, 15), (20, 4, 4), (20, 20, 30)]:
+        mc = t.Configurator(N_hor=N, Nstcobs=nst, Ndynobs=ndy)
+        c = mc.to_ttmpc()
+        p = t.scenes.make_scenes(64, c, seed=40 + N + nst, n_static=min(4, nst), n_dynamic=min(3, ndy),
+                                 blocking_fraction=0.2, mpc=mc)
+        sol = t.BatchSolver(c).run(p)
+        ref = O.solve_batch(c, p, threads=os.cpu_count(), warp=True)
+        assert_parity(sol, ref, 64)
+
+
 def test_warm_start_and_multipliers(cfg, solver):
     p = t.scenes.make_scenes(48, cfg, seed=17, n_static=2, n_dynamic=2)
     cold = solver.run(p)

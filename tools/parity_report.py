@@ -76,7 +76,7 @@ def workload_sample(name, n, seed=1000):
 def gpu_solve(cfg, p):
     s = t.BatchSolver(cfg)
     r = s.run(p)
-    return dict(u=np.asarray(r.u), cost=np.asarray(r.cost), exit_status=np.asarray(r.exit_status))
+    return dict(u=np.asarray(r.solution), cost=np.asarray(r.cost), exit_status=np.asarray(r.exit_status))
 
 
 def run(names, n, threads, use_gpu, n_dyn=None):

@@ -27,7 +27,7 @@ class TtmpcConfig(C.Structure):
         ("penalty_update_factor", C.c_double), ("inner_tolerance_update_factor", C.c_double),
         ("sufficient_decrease_coeff", C.c_double),
         ("lbfgs_memory", C.c_int), ("max_inner_iterations", C.c_int),
-        ("max_outer_iterations", C.c_int), ("_pad1", C.c_int),
+        ("max_outer_iterations", C.c_int), ("max_duration_ms", C.c_int),
     ]
 
 
@@ -104,6 +104,7 @@ SYMBOLS = {
     "ttmpc_launch_info": (_I, [_CFG, _I] + [C.POINTER(C.c_int)] * 5),
     "ttmpc_measure_fp64_peak": (_I, [C.POINTER(_D), _VP]),
     "ttmpc_probe_latency": (_I, [_CFG, _VP, C.POINTER(C.c_longlong), _I]),
+    "ttdqn_last_error": (C.c_char_p, []),
     "ttdqn_default_layout": (None, [_LAY]),
     "ttdqn_observe_act_device": (_I, [_LAY, _QN, _I] + [_VP] * 12 + [_VP]),
     "ttdqn_observe_act_host": (_I, [_LAY, _QN, _I] + [_VP] * 12),

@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(128) rl_ref_kernel(int n, int steps, double ts
 
 static thread_local std::string g_dqn_err;
 extern "C" const char *ttdqn_last_error(void) { return g_dqn_err.c_str(); }
-static int dfail(int code, const std::string &m) { g_dqn_err = m; return code; }
+namespace ttmpc { void set_last_error(const std::string &msg); }
+static int dfail(int code, const std::string &m) { g_dqn_err = m; ttmpc::set_last_error(m); return code; }
 #define DQN_TRY(x)                                                                   \
   do {                                                                               \
     cudaError_t e__ = (x);                                                           \

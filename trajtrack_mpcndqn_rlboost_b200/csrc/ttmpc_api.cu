@@ -20,6 +20,9 @@ using namespace ttmpc;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+// the DQN entry points (ttdqn.cu) report through the same per-thread string, so that
+// ttmpc_last_error() describes the last failure of ANY entry point of the library
+namespace ttmpc { void set_last_error(const std::string &msg) { g_err = msg; } }
 #define CUDA_TRY(x)                                                                     \
   do {                                                                                  \
     cudaError_t e__ = (x);                                                              \
@@ -58,6 +61,7 @@ extern "C" void ttmpc_default_config(ttmpc_config *c) {
   c->initial_penalty = 10.0; c->penalty_update_factor = 5.0;
   c->inner_tolerance_update_factor = 0.1; c->sufficient_decrease_coeff = 0.1;
   c->lbfgs_memory = 10; c->max_inner_iterations = 500; c->max_outer_iterations = 10;
+  c->max_duration_ms = 5000;  // MAX_SOVLER_TIME = 5_000_000 us (mpc_generator.py:22)
 }
 extern "C" int ttmpc_num_params(const ttmpc_config *c) {
   const int N = c->N_hor;
@@ -86,6 +90,7 @@ static int make_devcfg(const ttmpc_config *c, DevCfg *g) {
   g->N = N; g->Nother = c->Nother; g->Nstc = c->Nstcobs; g->nstcobs = c->nstcobs;
   g->ne = c->nstcobs / 3; g->Ndyn = c->Ndynobs; g->mem = c->lbfgs_memory;
   g->max_inner = c->max_inner_iterations; g->max_outer = c->max_outer_iterations;
+  g->max_ns = c->max_duration_ms > 0 ? (unsigned long long)c->max_duration_ms * 1000000ull : 0ull;
   g->off_s = 0; g->off_q = 2 * c->ns + c->nu; g->off_r = g->off_q + c->nq;
   g->off_vref = g->off_r + c->ns * N; g->off_c = g->off_vref + N;
   g->off_os = g->off_c + c->ns * N * c->Nother;
@@ -252,8 +257,17 @@ static int acquire_host_slot(Workspace **wout, Slot **out, int *busy_calls) {
 namespace {
 struct HostSlotLease {  // returns the slot when the host call ends, whatever the exit path
   Slot *s = nullptr;
+  bool clean = false;  // the call reached its end: both streams are known to be idle
   ~HostSlotLease() {
     if (!s) return;
+    if (!clean) {
+      // error exit: the gated kernel may still be waiting for chunks (it gives up after 2 s) and
+      // writing into the slot's buffers, copies may be in flight.  Nobody may reuse or free those
+      // buffers before the slot's streams have drained.
+      if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+      if (s->exec_stream) cudaStreamSynchronize(s->exec_stream);
+      cudaGetLastError();  // the failure was already reported to the caller
+    }
     { std::lock_guard<std::mutex> lk(g_mu); s->host_busy = false; }
     g_cv.notify_one();
   }
@@ -343,29 +357,45 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   if (n_scenes < 0 || !res || !res->u || (n_scenes > 0 && !d_p))
     return fail(TTMPC_ERR_BAD_ARG, "n_scenes >= 0, d_p and res->u are required");
   if (n_scenes == 0) return TTMPC_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
+  // The process-wide lock covers the bookkeeping only (workspace, the stream's slot, growing the
+  // slot's scratch buffers); the memsets and launches below run outside it, so several host threads
+  // / streams issue their solves concurrently.  One slot is used by one stream (or one host lease).
   Workspace *w;
-  rc = get_ws(&w);
-  if (rc) return rc;
-  // host path: the caller's slot (streamed inputs gated by its `ready` counter); device path:
-  // the slot of the stream
   Slot *sl = host_slot;
-  if (!sl) { rc = slot_for_stream(w, st, &sl); if (rc) return rc; }
   const int *d_ready = (host_slot && gated) ? host_slot->ready : nullptr;
   int grid;
-  rc = grid_for(w, g, n_scenes, &grid);
-  if (rc) return rc;
-  const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
   DevCfg gs = g;  // split kernel: clusters of (solver CTA, evaluator CTA)
   int clusters = 0;
-  if (use_split(g)) {
-    gs.warps_per_block = split_warps(g);
-    const long long want = ((long long)n_scenes + gs.warps_per_block - 1) / gs.warps_per_block;
-    clusters = (int)std::min<long long>(std::max(1, w->sm_count / 2), want);
+  bool want_order = false;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    rc = get_ws(&w);
+    if (rc) return rc;
+    // host path: the caller's slot (streamed inputs gated by its `ready` counter); device path:
+    // the slot of the stream
+    if (!sl) { rc = slot_for_stream(w, st, &sl); if (rc) return rc; }
+    rc = grid_for(w, g, n_scenes, &grid);
+    if (rc) return rc;
+    const size_t table = (size_t)DYN_FIELDS * g.Ndyn * g.N * sizeof(double);
+    if (use_split(g)) {
+      gs.warps_per_block = split_warps(g);
+      const long long want = ((long long)n_scenes + gs.warps_per_block - 1) / gs.warps_per_block;
+      clusters = (int)std::min<long long>(std::max(1, w->sm_count / 2), want);
+    }
+    rc = ensure_dyn(sl, (table ? table : 8) * std::max((size_t)grid * g.warps_per_block,
+                                                       (size_t)clusters * gs.warps_per_block));
+    if (rc) return rc;
+    // more scenes than resident warps: dispatch the likely-long ones first.  Not on the streamed
+    // host path (scenes become available in index order there).  TTMPC_NO_ORDER=1 disables it.
+    const char *no = std::getenv("TTMPC_NO_ORDER");
+    const long long resident = clusters > 0 ? (long long)clusters * gs.warps_per_block
+                                            : (long long)grid * g.warps_per_block;
+    want_order = !d_ready && n_scenes > resident && !(no && no[0] == '1');
+    if (want_order) {
+      rc = ensure_order(sl, 2 * (size_t)n_scenes + 64);
+      if (rc) return rc;
+    }
   }
-  rc = ensure_dyn(sl, (table ? table : 8) * std::max((size_t)grid * g.warps_per_block,
-                                                     (size_t)clusters * gs.warps_per_block));
-  if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(sl->work_counter, 0, sizeof(int), st));
   const char *nh = std::getenv("TTMPC_NO_HELPERS");
   SolveArgs A;
@@ -382,19 +412,10 @@ static int solve_device_impl(const ttmpc_config *cfg, int n_scenes, const double
   // the running average behind the early-helper threshold is per launch (workloads differ by 30x)
   if (A.run_stats) CUDA_TRY(cudaMemsetAsync(A.run_stats, 0, 2 * sizeof(unsigned long long), st));
   A.n_scenes = n_scenes; A.use_u0 = use_u0; A.use_y0 = use_y0;
-  // more scenes than resident warps: dispatch the likely-long ones first.  Not on the streamed
-  // host path (scenes become available in index order there).  TTMPC_NO_ORDER=1 disables it.
   A.order = nullptr;
-  {
-    const char *no = std::getenv("TTMPC_NO_ORDER");
-    const long long resident = clusters > 0 ? (long long)clusters * gs.warps_per_block
-                                            : (long long)grid * g.warps_per_block;
-    if (!d_ready && n_scenes > resident && !(no && no[0] == '1')) {
-      rc = ensure_order(sl, 2 * (size_t)n_scenes + 64);
-      if (rc) return rc;
-      CUDA_TRY(launch_rank_scenes(g, d_p, n_scenes, sl->order + n_scenes, sl->order, st));
-      A.order = sl->order;
-    }
+  if (want_order) {
+    CUDA_TRY(launch_rank_scenes(g, d_p, n_scenes, sl->order + n_scenes, sl->order, st));
+    A.order = sl->order;
   }
   // two builds of the same kernel, bit-identical results: unrolled hot loops when every scene has a
   // warp from the start (latency-bound), rolled loops when the batch queues behind the resident
@@ -696,6 +717,7 @@ extern "C" int ttmpc_solve_batch_host(const ttmpc_config *cfg, int n, const doub
   if (res->outer_iters) std::memcpy(res->outer_iters, hout, sizeof(int) * nn);
   if (res->inner_iters) std::memcpy(res->inner_iters, hin, sizeof(int) * nn);
   if (res->evals) std::memcpy(res->evals, hev, sizeof(long long) * 4 * nn);
+  lease.clean = true;
   return TTMPC_OK;
 }
 

@@ -75,6 +75,7 @@ struct DevCfg {
   double ts, inv_ts, h6, veh_d2, margin;
   double vmin, vmax, wmax, amin, amax, awmax;
   double tol, init_tol, delta_tol, c0, pen_factor, tol_factor, suff_dec;
+  unsigned long long max_ns;  // wall-clock budget of one scene [ns], 0 = none
 };
 
 // ---------------------------------------------------------------- sincos

@@ -14,6 +14,9 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 // This file is compiled twice (Makefile).  ttmpc_solve.o: hot loops unrolled -- lowest latency of a
 // single scene, ~47 KB of SASS per PANOC iteration.  ttmpc_solve_small.o (ttmpc_solve_small.cu,
@@ -31,6 +34,7 @@
 #ifdef TTMPC_SMALL_CODE
 #define solve_kernel solve_kernel_small
 #define launch_solve launch_solve_small
+#define solve_occupancy_impl solve_occupancy_small_impl
 #endif
 
 namespace ttmpc {
@@ -178,7 +182,10 @@ struct CtaHelp {
   int epoch[8];   // serial number of warp w's current scene (a helper serves one scene)
 };
 struct HelpCtl {
-  bool enabled;              // helpers exist in this launch and have not timed out on this scene
+  bool enabled;              // helpers exist in this launch and none has timed out on this warp
+  bool timed_out;            // a request was abandoned after the time-out: helpers stay off for this
+                             // warp until the launch ends, and the abandoned request is waited for
+                             // before the scene tables are re-staged (see solve_kernel)
   volatile int *slot;        // &cta->helper[me]
   bool pending;              // a posted request has not been collected yet
   // split kernel (solver CTA): this warp's evaluator mailbox in the peer CTA's shared memory
@@ -282,6 +289,7 @@ __device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int l
   hc.pending = false;
   if (!ok) {
     hc.enabled = false;
+    hc.timed_out = true;
     if (SP && lane == 0 && hc.fail) atomicExch(hc.fail, 1);
     return false;
   }
@@ -726,7 +734,13 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
   unsigned long long panoc_iters = 0;
   const double SMALL_EPSILON = 2.220446049250313e-16;
 
+  bool in_time = true;  // OpEn: max_duration (AlmOptimizer::solve / PANOCOptimizer::solve)
   for (int outer = 1; outer <= g.max_outer; outer++) {
+    if (g.max_ns) {  // no time left before this outer iteration: NotConvergedOutOfTime
+      unsigned long long el = globaltimer_ns() - t_start;
+      el = __shfl_sync(FULL, el, 0);
+      if (el > g.max_ns) { exit_status = TTMPC_NOT_CONVERGED_OUT_OF_TIME; in_time = false; break; }
+    }
     num_outer++;
     pb.ya = clipd(pb.ya, -1e12, 1e12);
     pb.yw = clipd(pb.yw, -1e12, 1e12);
@@ -776,14 +790,20 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
           else
             flag = panoc_step<DM, false, false>(g, sm, lane, pb, z, U, g.tol, hc);
         }
-        if (!(flag && cont)) break;
+        if (!(flag && cont && in_time)) break;
         num_iter++;
         cont = num_iter < g.max_inner;
+        if (g.max_ns) {
+          unsigned long long el = globaltimer_ns() - t_start;
+          el = __shfl_sync(FULL, el, 0);
+          in_time = el <= g.max_ns;
+        }
       }
       const bool finite = isfinite(z.u0) && isfinite(z.u1);
       if (!__all_sync(FULL, finite)) { exit_status = TTMPC_NOT_FINITE; inner_count += num_iter; break; }
       z.u0 = z.h0; z.u1 = z.h1;
-      inner_status = cont ? TTMPC_CONVERGED : TTMPC_NOT_CONVERGED_ITERATIONS;
+      inner_status = !cont ? TTMPC_NOT_CONVERGED_ITERATIONS
+                           : (!in_time ? TTMPC_NOT_CONVERGED_OUT_OF_TIME : TTMPC_CONVERGED);
       inner_count += num_iter;
       panoc_iters += num_iter;
       last_fpr = U.norm_fpr;
@@ -832,7 +852,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     f2_norm = f2_norm_plus;
     pb.ya = yp_a; pb.yw = yp_w;
   }
-  if (exit_status != TTMPC_NOT_FINITE && num_outer == g.max_outer)
+  if (exit_status != TTMPC_NOT_FINITE && in_time && num_outer == g.max_outer)
     exit_status = TTMPC_NOT_CONVERGED_ITERATIONS;
 
   help_drain<SP>(hc, sm, lane, N);  // no evaluation on this scene's tables may still be in flight
@@ -903,6 +923,7 @@ __global__ void __launch_bounds__(128, TTMPC_MIN_BLOCKS) solve_kernel(const __gr
   __syncthreads();
   HelpCtl hc;
   hc.enabled = A.helpers != 0;
+  hc.timed_out = false;
   hc.slot = &cta->helper[warp];
   hc.pending = false;
   hc.r_hreq = nullptr; hc.r_yrow = nullptr; hc.r_hdr = nullptr; hc.fail = nullptr; hc.phase = 0; hc.peer_rank = 0;
@@ -924,6 +945,23 @@ __global__ void __launch_bounds__(128, TTMPC_MIN_BLOCKS) solve_kernel(const __gr
       *reinterpret_cast<volatile int *>(&cta->epoch[warp]) = cta->epoch[warp] + 1;
       *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 1;
     }
+    if (__builtin_expect(hc.timed_out, 0)) {
+      // A request of an earlier scene was abandoned (the helper did not answer within the time-out:
+      // the context was preempted or time-sliced).  The helper may still be evaluating on this
+      // warp's tables: it detaches when it sees busy == 0 / a new epoch, so wait (bounded) until the
+      // helper slot is empty or the abandoned request has been answered, then clear the mailbox.
+      if (lane == 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        const volatile int *stp = reinterpret_cast<volatile int *>(&sm.hhdr->state);
+        while (*reinterpret_cast<volatile int *>(&cta->helper[warp]) >= 0 && *stp == 1) {
+          __nanosleep(1000);
+          if (globaltimer_ns() - t0 > 5000000000ull) break;
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 0;  // mailbox empty at scene start
+    __syncwarp();
     if (A.ready) {  // parameters of this scene may still be on their way from the host
       int ok = 1;
       if (lane == 0) {
@@ -950,7 +988,7 @@ __global__ void __launch_bounds__(128, TTMPC_MIN_BLOCKS) solve_kernel(const __gr
 #ifdef TTMPC_PROFILE_STAGE
     if (lane == 0 && A.eprof) atomicAdd(A.eprof + 9, (unsigned long long)(clock64() - t_stage0));  // staging cycles (slot of the apply timer)
 #endif
-    hc.enabled = A.helpers != 0;
+    hc.enabled = A.helpers != 0 && !hc.timed_out;
     solve_scene<DM, false>(g, sm, A, scene, lane, wstats, hc);
     if (lane == 0) {
       *reinterpret_cast<volatile int *>(&cta->busy[warp]) = 0;
@@ -1111,7 +1149,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   unsigned long long wstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (rank == 0) {
     HelpCtl hc;
-    hc.enabled = true; hc.slot = nullptr; hc.pending = false; hc.phase = 0; hc.peer_rank = 1;
+    hc.enabled = true; hc.timed_out = false; hc.slot = nullptr; hc.pending = false; hc.phase = 0; hc.peer_rank = 1;
     hc.r_hreq = peer.hreq; hc.r_yrow = peer.yrow; hc.r_hdr = peer.hhdr; hc.fail = A.timeout_flag;
     const int N = g.N;
     while (true) {
@@ -1295,22 +1333,85 @@ static bool is_default_dims(const DevCfg &g) {
   return g.N == 20 && g.Nother == 10 && g.Nstc == 10 && g.ne == 4 && g.Ndyn == 15 && g.mem == 10;
 }
 
+// cudaFuncSetAttribute / occupancy queries cost microseconds each and used to run on every call
+// (they matter for the one-scene latency path): both are cached per (kernel, device).
+static std::mutex g_attr_mu;
+static std::map<std::pair<const void *, int>, size_t> g_attr_smem;
+static std::map<std::tuple<const void *, int, int, size_t>, int> g_attr_occ;
 template <class K>
 static cudaError_t set_smem(K kernel, size_t smem) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const auto key = std::make_pair(reinterpret_cast<const void *>(kernel), dev);
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    auto it = g_attr_smem.find(key);
+    if (it != g_attr_smem.end() && it->second >= smem) return cudaSuccess;
+  }
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    size_t &v = g_attr_smem[key];
+    if (v < smem) v = smem;
+  }
+  return e;
+}
+template <class K>
+static cudaError_t cached_occupancy(K kernel, int block, size_t smem, int *blocks_per_sm) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const auto key = std::make_tuple(reinterpret_cast<const void *>(kernel), dev, block, smem);
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    auto it = g_attr_occ.find(key);
+    if (it != g_attr_occ.end()) { *blocks_per_sm = it->second; return cudaSuccess; }
+  }
+  if ((e = set_smem(kernel, smem)) != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, block, smem);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    g_attr_occ[key] = *blocks_per_sm;
+  }
+  return e;
+}
+
+// Shapes with a fully specialised solve kernel: config/mpc_default.yaml and the horizon /
+// obstacle-count sweep of BASELINE configs[4]; everything else runs the run-time-dimension build.
+//        N  Nother Nstc ne Ndyn mem
+#define TTMPC_SOLVE_SHAPES(X) \
+  X(20, 10, 10, 4, 15, 10)    \
+  X(10, 10, 10, 4, 15, 10)    \
+  X(32, 10, 10, 4, 15, 10)    \
+  X(20, 10, 4, 4, 4, 10)      \
+  X(20, 10, 20, 4, 30, 10)
+template <class F>
+static cudaError_t with_solve_dims(const DevCfg &g, F &&f) {
+#define X(n, no, ns, e, nd, m) \
+  if (g.N == n && g.Nother == no && g.Nstc == ns && g.ne == e && g.Ndyn == nd && g.mem == m) return f(Dims<n, no, ns, e, nd, m>{});
+  TTMPC_SOLVE_SHAPES(X)
+#undef X
+  return f(DimsRuntime{});
 }
 
 cudaError_t launch_solve(const DevCfg &g, const SolveArgs &A, int grid, cudaStream_t st) {
   const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block + sizeof(CtaHelp);
-  cudaError_t e;
-  if (is_default_dims(g)) {
-    if ((e = set_smem(solve_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
-    solve_kernel<DimsDefault><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
-  } else {
-    if ((e = set_smem(solve_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
-    solve_kernel<DimsRuntime><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
-  }
-  return cudaGetLastError();
+  return with_solve_dims(g, [&](auto dm) -> cudaError_t {
+    using DM = decltype(dm);
+    cudaError_t e;
+    if ((e = set_smem(solve_kernel<DM>, smem)) != cudaSuccess) return e;
+    solve_kernel<DM><<<grid, g.warps_per_block * 32, smem, st>>>(g, A);
+    return cudaGetLastError();
+  });
+}
+// resident blocks per SM of the kernel launch_solve would pick
+cudaError_t solve_occupancy_impl(const DevCfg &g, int *blocks_per_sm) {
+  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block + sizeof(CtaHelp);
+  return with_solve_dims(g, [&](auto dm) -> cudaError_t {
+    using DM = decltype(dm);
+    return cached_occupancy(solve_kernel<DM>, g.warps_per_block * 32, smem, blocks_per_sm);
+  });
 }
 #ifndef TTMPC_SMALL_CODE
 // clusters of (solver CTA, evaluator CTA); g.warps_per_block warps each
@@ -1348,18 +1449,7 @@ cudaError_t launch_eval(const DevCfg &g, const EvalArgs &A, int grid, cudaStream
   }
   return cudaGetLastError();
 }
-cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm) {
-  const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block + sizeof(CtaHelp);
-  cudaError_t e;
-  if (is_default_dims(g)) {
-    if ((e = set_smem(solve_kernel<DimsDefault>, smem)) != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<DimsDefault>,
-                                                         g.warps_per_block * 32, smem);
-  }
-  if ((e = set_smem(solve_kernel<DimsRuntime>, smem)) != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_kernel<DimsRuntime>,
-                                                       g.warps_per_block * 32, smem);
-}
+cudaError_t solve_occupancy(const DevCfg &g, int *blocks_per_sm) { return solve_occupancy_impl(g, blocks_per_sm); }
 cudaError_t launch_probe(const DevCfg &g, const double *p, double *dyn, long long *out, int reps,
                          cudaStream_t st) {
   const size_t smem = (size_t)g.smem_per_warp * g.warps_per_block;

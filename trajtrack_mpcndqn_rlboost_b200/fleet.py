@@ -182,8 +182,18 @@ class FleetPlanner:
         r.inner_iters, r.y, r.pred_states = self.inner.data_ptr(), self.y.data_ptr(), self.pred_states.data_ptr()
         return r
 
-    def step(self, keep_multipliers: bool = False, stream=None):
-        """One control step of every robot, asynchronous on the current torch stream."""
+    def step(self, keep_multipliers: bool = True, stream=None):
+        """One control step of every robot, asynchronous on the current torch stream.
+
+        keep_multipliers=True (default) is what the reference's control loop does: the PyO3 ``Solver``
+        object of a robot owns its AlmCache, so the Lagrange multipliers one ``run()`` ends with are
+        the ones the next ``run()`` starts from (``self.y`` lives on the device between steps and is
+        passed in / out of the solve).  False starts every step from y = 0 (a fresh solver object).
+
+        ``pred_states`` is the rollout of u* from the state the step STARTED in (p.s), i.e. one step
+        earlier than ``TrajectoryGenerator.run_step``'s list, which re-applies u from the post-step
+        state (trajectory_generator.py:296-301; ``planner.TrajectoryGenerator`` reproduces that list
+        on the host)."""
         st = stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
         f, r = self._fleet_struct(), self._result_struct()
         _lib.check(self.lib.ttmpc_fleet_step_device(C.byref(self.cfg), C.byref(f), self.p.data_ptr(),

@@ -16,6 +16,7 @@ SOLVER_DEFAULTS = dict(
     penalty_update_factor=5.0, inner_tolerance_update_factor=0.1,
     sufficient_decrease_coeff=0.1, lbfgs_memory=10, max_inner_iterations=500,
     max_outer_iterations=10,
+    max_duration_ms=5000,  # MAX_SOVLER_TIME = 5_000_000 us (mpc_generator.py:22, 270); 0 = no limit
 )
 
 # config/mpc_default.yaml of the reference, so that synthetic benches do not need the file
