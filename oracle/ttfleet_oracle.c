@@ -61,6 +61,9 @@ static double poly_distance(const double *xy, int nv, double px, double py) {
   }
   return best;
 }
+/* exported for tests/test_geometry_independent.py (checked against dense sampling + winding number) */
+int ttfleet_oracle_poly_contains(const double *xy, int nv, double px, double py) { return poly_contains(xy, nv, px, py); }
+double ttfleet_oracle_poly_distance(const double *xy, int nv, double px, double py) { return poly_distance(xy, nv, px, py); }
 /* HintSwitcher.switch (main_pre.py:35-52) for robot e; ref rows are the ORIGINAL local reference */
 static int hint_switch(const ttmpc_fleet *f, int e, int N, const double *ref, int L, int idx) {
   int *st = f->sw_state + 2 * e;   /* switch_on, detach_cnt */

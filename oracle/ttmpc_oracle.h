@@ -78,6 +78,10 @@ void ttfleet_oracle_pack(const ttmpc_config *cfg, const ttmpc_fleet *fleet, doub
 void ttfleet_oracle_advance(const ttmpc_config *cfg, const ttmpc_fleet *fleet, const double *u,
                             const int *exit_status, int use_libm);
 
+/* shapely Polygon.contains(Point) / Polygon.distance(Point) as HintSwitcher uses them (main_pre.py:35-52) */
+int ttfleet_oracle_poly_contains(const double *xy, int nv, double px, double py);
+double ttfleet_oracle_poly_distance(const double *xy, int nv, double px, double py);
+
 /* DQN companion oracle: one env. */
 void ttdqn_oracle_observe(const ttdqn_scene_layout *lay, const double *agent,
                           const double *poly_xy, const int *poly_off,

@@ -52,12 +52,16 @@ def load():
         lib.ttmpc_oracle_eval_warp.argtypes = [CFG, VP, VP, D, VP, VP, VP, VP, VP]
         lib.ttmpc_oracle_sincos.argtypes = [D, C.POINTER(D), C.POINTER(D)]
         lib.ttdqn_oracle_observe_act.argtypes = [C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet), I] + [VP] * 12
+        lib.ttdqn_oracle_observe.argtypes = [C.POINTER(TtdqnLayout), VP, VP, VP, VP, I, VP, VP]
         lib.ttdqn_oracle_project.argtypes = [VP, I, D, D]
         lib.ttdqn_oracle_project.restype = D
         lib.ttdqn_oracle_internal_obs.argtypes = [I, D, D, VP, VP, I, VP, VP]
         lib.ttdqn_oracle_rl_ref.argtypes = [I, D, D, VP, I, VP, I]
         lib.ttfleet_oracle_pack.argtypes = [CFG, C.POINTER(TtmpcFleet), VP, I]
         lib.ttfleet_oracle_advance.argtypes = [CFG, C.POINTER(TtmpcFleet), VP, VP, I]
+        lib.ttfleet_oracle_poly_contains.argtypes = [VP, I, D, D]
+        lib.ttfleet_oracle_poly_distance.argtypes = [VP, I, D, D]
+        lib.ttfleet_oracle_poly_distance.restype = D
         _lib = lib
     return _lib
 
@@ -241,3 +245,23 @@ def rl_ref(agent5, action, steps=20, ts=0.2, ref_speed=1.0, use_libm=True):
     out = np.zeros((steps, 2))
     lib.ttdqn_oracle_rl_ref(steps, ts, ref_speed, _p(a), int(action), _p(out), 1 if use_libm else 0)
     return out
+
+
+def poly_contains(xy, px, py):
+    xy = np.ascontiguousarray(xy, np.float64)
+    return bool(load().ttfleet_oracle_poly_contains(_p(xy), len(xy), float(px), float(py)))
+
+
+def poly_distance(xy, px, py):
+    xy = np.ascontiguousarray(xy, np.float64)
+    return float(load().ttfleet_oracle_poly_distance(_p(xy), len(xy), float(px), float(py)))
+
+
+def observe(lay, agent, rings, solid):
+    """Sector / ray distances of ONE environment (ttdqn_oracle_observe): rings = list of [nv,2] arrays."""
+    from trajtrack_mpcndqn_rlboost_b200.dqn import pack_geometry
+    xy, off, sol, cnt = pack_geometry(lay, [rings], [solid])
+    agent = np.ascontiguousarray(agent, np.float64)
+    seg = np.zeros(lay.num_segments); ray = np.zeros(lay.num_segments)
+    load().ttdqn_oracle_observe(C.byref(lay), _p(agent), _p(xy[0]), _p(off[0]), _p(sol[0]), int(cnt[0]), _p(seg), _p(ray))
+    return seg, ray
