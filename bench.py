@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=6, help="batches in flight (1 = one at a time)")
     ap.add_argument("--batches", type=int, default=4, help="distinct input batches the steps rotate through")
+    ap.add_argument("--quick", action="store_true", help="sweep rows: skip the sequential / pageable / one-scene legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -261,7 +262,8 @@ def main():
     # ---------------- one batch at a time ("sequential"): per-batch latency.  Each step is timed by
     # its own event pair, L2 flushed before it; the next step starts when this one has ended.
     seq_ms = []
-    for it in range(args.warmup + args.steps):
+    seq_steps = 2 if args.quick else args.steps
+    for it in range(args.warmup + seq_steps):
         if it == args.warmup:
             barrier()
         flush.zero_()
@@ -361,9 +363,12 @@ def main():
 
     e2e_step = e2e_leg(p_pins, D, args.steps)
     e2e_value = total_scenes / e2e_step
-    e2e_pageable_step = e2e_leg(p_hosts, D, args.steps)
-    # one call at a time (latency of the blocking call)
-    e2e_seq_step = e2e_leg(p_pins, 1, min(args.steps, 8))
+    if args.quick:
+        e2e_pageable_step = e2e_seq_step = float("nan")
+    else:
+        e2e_pageable_step = e2e_leg(p_hosts, D, args.steps)
+        # one call at a time (latency of the blocking call)
+        e2e_seq_step = e2e_leg(p_pins, 1, min(args.steps, 8))
     h2d = p_host.nbytes
     N = cfg.N_hor
     d2h = n * (2 * 2 * N * 8 + 5 * 8 + N * 3 * 8 + 3 * 4 + 4 * 8)
@@ -425,7 +430,7 @@ def main():
     try:
         one = solver.alloc_device(1, device=dev)
         ts = []
-        for i in range(48):
+        for i in range(0 if args.quick else 48):
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
             a.record(main_stream)
             solver.run_device(p_devs[0][i:i + 1], one)
@@ -434,7 +439,8 @@ def main():
             if i >= 8:
                 ts.append(a.elapsed_time(b))
         ts.sort()
-        latency.update({"one_scene_p50_ms": ts[len(ts) // 2], "one_scene_max_ms": ts[-1], "one_scene_samples": len(ts)})
+        if ts:
+            latency.update({"one_scene_p50_ms": ts[len(ts) // 2], "one_scene_max_ms": ts[-1], "one_scene_samples": len(ts)})
     except Exception as e:  # a diagnostic must never cost the bench line
         latency["one_scene_error"] = repr(e)
 

@@ -24,9 +24,15 @@ def _worker(rank, world, port, out_dir):
     import bench
     import trajtrack_mpcndqn_rlboost_b200 as t
     from tests import oracle_lib as O
-    # the shard bench.py builds for this rank (different seed per rank, same shapes)
+    # what bench.py builds: the same R seeded batches on every rank, rank r starting its rotation at
+    # batch r (equal work on every rank over K = multiple of R steps, different scenes at any one step)
     t.scenes.WORKLOADS["tiny"] = dict(n=6, n_static=2, n_dynamic=1, blocking_fraction=0.0, solver={})
-    cfg, p, w = bench.build_workload("tiny", rank, world)
+    R = 2
+    batches = [bench.build_workload("tiny", rank, world, j)[1] for j in range(R)]
+    cfg = bench.build_workload("tiny", rank, world, 0)[0]
+    rot = rank % R
+    p = batches[(0 + rot) % R]            # the batch of step 0 on this rank
+    np.save(os.path.join(out_dir, f"all{rank}.npy"), np.stack(batches))
     sol = O.solve_batch(cfg, p, warp=True)
     # max-over-ranks timing + gathered metrics, like bench.py
     tns = torch.tensor([float(rank + 1)], dtype=torch.float64)
@@ -47,7 +53,10 @@ def test_two_rank_sharding(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     p0, p1 = np.load(tmp_path / "p0.npy"), np.load(tmp_path / "p1.npy")
     assert p0.shape == p1.shape == (6, 2658)
-    assert not np.array_equal(p0, p1)                    # every rank owns different scenes
+    assert not np.array_equal(p0, p1)                    # at one step the ranks solve different scenes
+    a0, a1 = np.load(tmp_path / "all0.npy"), np.load(tmp_path / "all1.npy")
+    assert np.array_equal(a0, a1)                         # ... drawn from the same seeded batches
+    assert np.array_equal(p0, a0[0]) and np.array_equal(p1, a0[1])   # rotation offset = rank
     assert float(np.load(tmp_path / "max.npy")[0]) == 2.0  # max over ranks
     hist = np.load(tmp_path / "hist.npy")
     assert hist.shape == (2, 4) and hist.sum() == 12      # all 12 scenes accounted for
