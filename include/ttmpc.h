@@ -136,7 +136,11 @@ typedef struct ttmpc_result {
   double *f2_norm;      /* [n]                                                      */
   double *penalty;      /* [n]  final c                                             */
   double *y;            /* [n][2*N] in: initial multipliers (see use_y0), out: final */
-  double *pred_states;  /* [n][N][ns] rollout of u* from p.s (trajectory_generator.py:296-301) */
+  double *pred_states;  /* [n][N][ns] rollout of u* from p.s, i.e. from the state the solve STARTED in.
+                           NOTE: the reference's list (trajectory_generator.py:296-301) starts from the
+                           state AFTER u[0] was applied (taken_states[-1]) and re-applies u from there, so
+                           it is this rollout shifted by one step; the Python TrajectoryGenerator mirror
+                           rebuilds the reference's list on the host from u.                          */
   long long *evals;     /* [n][4] cost-only evals, cost+gradient evals, solve time [ns],
                            solve start [ns, %globaltimer] (diagnostics)              */
 } ttmpc_result;

@@ -15,3 +15,8 @@ TTMPC_NO_STREAM=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-contr
 python bench.py > gpurun_out/r2_bench_static4096.json 2> gpurun_out/r2_bench_static4096.err; echo "bench rc $?"; tail -c 400 gpurun_out/r2_bench_static4096.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/r2_bench_reference.json
 python tools/parity_report.py --gpu --n 512 --n-dynamic 96 --out gpurun_out/r2_parity_distribution_gpu.json > gpurun_out/r2_parity_gpu.md 2>&1; tail -8 gpurun_out/r2_parity_gpu.md
+python tools/bench_qnet.py > gpurun_out/r2_qnet.json 2>/dev/null; cat gpurun_out/r2_qnet.json
+python tools/single_latency.py > gpurun_out/r2_single_latency.txt 2>/dev/null; cat gpurun_out/r2_single_latency.txt
+rm -f gpurun_out/bench_fleet.json gpurun_out/bench_hybrid.json
+python tools/bench_fleet.py 4096 > /dev/null 2>&1; python tools/bench_fleet.py 16384 > /dev/null 2>&1; cp gpurun_out/bench_fleet.json gpurun_out/r2_fleet.json; cut -c1-300 gpurun_out/r2_fleet.json
+python tools/bench_hybrid.py > /dev/null 2>&1; cp gpurun_out/bench_hybrid.json gpurun_out/r2_hybrid.json; cut -c1-400 gpurun_out/r2_hybrid.json
