@@ -64,7 +64,7 @@ def main():
         comp.observe_act_device(fp.state, xy, off, sol, cnt, internal, old, out, qs)
         t.dqn.rl_ref_device(agent5, out["action"], steps=fp.N, ts=mc.ts, ref_speed=1.0, out=rl)
         e[1].record()
-        fp.step()
+        fp.step(keep_multipliers=os.environ.get('KEEP_Y', '1') == '1')
         e[2].record()
         if times is not None:
             torch.cuda.synchronize()

@@ -21,7 +21,10 @@ def num(k):
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
     return x * scale
 dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-fl = 2 * num("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum") + num("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum") + num("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
+# --set full carries the per-cycle rates (sum over the SMSPs / elapsed cycles): x elapsed cycles = totals
+cyc = num("smsp__cycles_elapsed.avg") if "smsp__cycles_elapsed.avg" in d else num("sm__cycles_elapsed.avg")
+rate = lambda op: num(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed")
+fl = (2 * rate("dfma") + rate("dadd") + rate("dmul")) * cyc
 path = os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")
 cur = json.load(open(path)) if os.path.exists(path) else {}
 cur[wl] = {"dram_bytes_per_launch": dram, "executed_flops_per_launch": fl, "evals_per_launch": evals,

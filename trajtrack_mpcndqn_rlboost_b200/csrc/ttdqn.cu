@@ -31,6 +31,7 @@
 #include <math.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <string>
 
 #include "../../include/ttmpc.h"
@@ -576,11 +577,30 @@ extern "C" int ttdqn_observe_act_device(const ttdqn_scene_layout *lay, const ttd
   A.action = d_action; A.seg_dist = d_seg; A.ray_dist = d_ray; A.n_envs = n;
   // tensor-core path of the Q-network: 16-wide hidden layers, up to 16 outputs (the reference's
   // SB3 [16, 16] MLP); TTDQN_QNET=fma forces the FMA-pipe path for A/B measurements
+  int dev = 0, sms = 0;
+  DQN_TRY(cudaGetDevice(&dev));
   bool mma = qn && qn->n_h1 == 16 && qn->n_h2 == 16 && qn->n_out <= 16 && qn->n_in <= 248;
   if (const char *e = std::getenv("TTDQN_QNET")) mma = mma && !(e[0] == 'f');
   A.obs = nullptr; A.obs_stride = (A.n_in + 7) / 8 * 8; A.defer_net = 0;
   float *d_obs = nullptr;
   if (mma) {
+    // stream-ordered scratch from the device's default memory pool.  The pool's default release
+    // threshold is 0 (memory goes back to the OS at every synchronisation and the next call pays
+    // milliseconds to get it again): raise it once per device.
+    {
+      static std::mutex mu;
+      static bool raised[64] = {};
+      std::lock_guard<std::mutex> lk(mu);
+      if (dev >= 0 && dev < 64 && !raised[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        raised[dev] = true;
+      }
+    }
     DQN_TRY(cudaMallocAsync((void **)&d_obs, sizeof(float) * (size_t)n * A.obs_stride, (cudaStream_t)stream));
     A.obs = d_obs; A.defer_net = 1;
   }
@@ -588,8 +608,6 @@ extern "C" int ttdqn_observe_act_device(const ttdqn_scene_layout *lay, const ttd
   size_t wbytes = ((size_t)(A.n_in * A.n_h1 + A.n_h1 + A.n_h1 * A.n_h2 + A.n_h2 + A.n_h2 * A.n_out + A.n_out) * sizeof(float) + 15) / 16 * 16;
   size_t per_warp = (sizeof(Sector) * MAX_SEG + sizeof(float) * (size_t)(A.n_in + A.n_h1 + A.n_h2 + A.n_out + 4) + 15) / 16 * 16;
   size_t smem = wbytes + per_warp * warps;
-  int dev = 0, sms = 0;
-  DQN_TRY(cudaGetDevice(&dev));
   DQN_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   DQN_TRY(cudaFuncSetAttribute(observe_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
