@@ -31,6 +31,9 @@
 // scene alone is 15 % faster (1.50 -> 1.30 ms p50) and a 4096-scene batch alone 9 % (24.0 -> 21.8 ms).
 #define TTMPC_MIN_BLOCKS 2
 #endif
+#ifndef TTMPC_MAX_THREADS
+#define TTMPC_MAX_THREADS 128  // CTA size the register budget is computed for (the API launches 64)
+#endif
 #ifdef TTMPC_SMALL_CODE
 #define solve_kernel solve_kernel_small
 #define launch_solve launch_solve_small
@@ -911,7 +914,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
 }
 
 template <class DM>
-__global__ void __launch_bounds__(128, TTMPC_MIN_BLOCKS) solve_kernel(const __grid_constant__ DevCfg g,
+__global__ void __launch_bounds__(TTMPC_MAX_THREADS, TTMPC_MIN_BLOCKS) solve_kernel(const __grid_constant__ DevCfg g,
                                                     const __grid_constant__ SolveArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
