@@ -192,7 +192,9 @@ def main():
     ap.add_argument("--workload", default="static4096")
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight (1 = one at a time)")
+    ap.add_argument("--depth", type=int, default=0,
+                    help="batches in flight (1 = one at a time; 0 = auto: the divisor of --steps closest to 6 in 4..8, "
+                         "so that every stream carries the same number of steps and the region does not end with one or two streams still busy)")
     ap.add_argument("--batches", type=int, default=4, help="distinct input batches the steps rotate through")
     ap.add_argument("--quick", action="store_true", help="sweep rows: skip the sequential / pageable / one-scene legs")
     args = ap.parse_args()
@@ -230,6 +232,9 @@ def main():
     lib = _lib.load()
     dev = torch.device("cuda", local)
     p_devs = [torch.from_numpy(p).pin_memory().to(dev, non_blocking=True) for p in p_hosts]
+    if args.depth <= 0:  # equal number of steps per stream: 20 steps -> 5 streams x 4 (6 streams would leave 2 of them a 4th step)
+        cand = [d for d in (6, 5, 7, 8, 4) if args.steps % d == 0]
+        args.depth = cand[0] if cand else 6
     D = max(1, args.depth)
     bufs_ring = [solver.alloc_device(n, device=dev) for _ in range(D)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
