@@ -239,10 +239,21 @@ TT_SCAN_FN D2 wsuffix2v(double a, double b) {
   return r;
 }
 __device__ __forceinline__ void wsuffix2(double &a, double &b) { const D2 r = wsuffix2v(a, b); a = r.a; b = r.b; }
+// v + v[lane ^ O] (the 64-bit shuffle intrinsic costs two extra moves per use)
+template <int O>
+__device__ __forceinline__ double xor_get(double v) {
+  double t;
+  asm volatile("{\n\t.reg .b32 lo, hi, tl, th;\n\t"
+               "mov.b64 {lo, hi}, %1;\n\t"
+               "shfl.sync.bfly.b32 tl, lo, %2, 31, 0xffffffff;\n\t"
+               "shfl.sync.bfly.b32 th, hi, %2, 31, 0xffffffff;\n\t"
+               "mov.b64 %0, {tl, th};\n\t}"
+               : "=d"(t) : "d"(v), "n"(O));
+  return t;
+}
 // all-reduce of one value: xor-butterfly, offsets 16 .. 1
 __device__ __forceinline__ double wsum_inl(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  v += xor_get<16>(v); v += xor_get<8>(v); v += xor_get<4>(v); v += xor_get<2>(v); v += xor_get<1>(v);
   return v;
 }
 static __device__ __noinline__ double wsum(double v) { return wsum_inl(v); }
@@ -251,12 +262,11 @@ __device__ __forceinline__ void wsum4_inl(double &a, double &b, double &c, doubl
   const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
   double x = b4 ? c : a, y = b4 ? d : b;
   const double sx = b4 ? a : c, sy = b4 ? b : d;
-  x += __shfl_xor_sync(FULL, sx, 16); y += __shfl_xor_sync(FULL, sy, 16);
+  x += xor_get<16>(sx); y += xor_get<16>(sy);
   double z = b3 ? y : x;
   const double sz = b3 ? x : y;
-  z += __shfl_xor_sync(FULL, sz, 8);
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) z += __shfl_xor_sync(FULL, z, o);
+  z += xor_get<8>(sz);
+  z += xor_get<4>(z); z += xor_get<2>(z); z += xor_get<1>(z);
   a = __shfl_sync(FULL, z, 0); b = __shfl_sync(FULL, z, 8);
   c = __shfl_sync(FULL, z, 16); d = __shfl_sync(FULL, z, 24);
 }
