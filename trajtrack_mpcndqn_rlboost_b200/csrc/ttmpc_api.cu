@@ -304,8 +304,12 @@ static int ensure_staging(Slot *w, size_t bytes) {
     w->dbuf = nullptr; w->dbytes = 0;
     CUDA_TRY(cudaMalloc(&w->dbuf, bytes));
     // the fields of the result block are padded apart and come back in ONE device-to-host copy:
-    // define the padding once (compute-sanitizer initcheck reads the copy source)
-    CUDA_TRY(cudaMemset(w->dbuf, 0, bytes));
+    // define the padding once (compute-sanitizer initcheck reads the copy source).  ON THE SLOT'S COPY
+    // STREAM: the slot's streams are non-blocking, a memset on the legacy stream is not ordered with
+    // them and would race the input copies that follow (it did: zeroed parameter chunks).  The exec
+    // stream waits for ev_inputs, which is recorded on the copy stream after this.
+    if (w->copy_stream) CUDA_TRY(cudaMemsetAsync(w->dbuf, 0, bytes, w->copy_stream));
+    else { CUDA_TRY(cudaMemset(w->dbuf, 0, bytes)); CUDA_TRY(cudaDeviceSynchronize()); }
     w->dbytes = bytes;
   }
   if (bytes > w->hbytes) {
