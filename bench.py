@@ -196,9 +196,9 @@ def main():
                     help="batches in flight (1 = one at a time; 0 = auto: the divisor of --steps closest to 6 in 4..8, "
                          "so that every stream carries the same number of steps and the region does not end with one or two streams still busy)")
     ap.add_argument("--batches", type=int, default=4, help="distinct input batches the steps rotate through")
-    ap.add_argument("--e2e-depth", type=int, default=6,
-                    help="host calls in flight in the e2e leg (run_many threads take the next batch when theirs returns, "
-                         "so there is no divisor effect; more calls than streams hide the host-side gaps between calls)")
+    ap.add_argument("--e2e-depth", type=int, default=0,
+                    help="host calls in flight in the e2e leg (0 = the same number as --depth; measured on one B200 with "
+                         "20 steps, tools/e2e_ab.py: 5 calls 552 k, 6 calls 537 k, 7 calls 530 k, 8 calls 527 k solves/s)")
     ap.add_argument("--quick", action="store_true", help="sweep rows: skip the sequential / pageable / one-scene legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -369,7 +369,7 @@ def main():
             assert np.array_equal(hs.exit_status, status[(it + rot) % R]), "host and device paths disagree"
         return max_over_ranks(dt / steps)
 
-    DE = max(1, min(8, args.e2e_depth))
+    DE = max(1, min(8, args.e2e_depth if args.e2e_depth > 0 else D))
     e2e_step = e2e_leg(p_pins, DE, args.steps)
     e2e_value = total_scenes / e2e_step
     if args.quick:
