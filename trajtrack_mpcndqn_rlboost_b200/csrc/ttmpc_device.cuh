@@ -391,6 +391,7 @@ struct Dims {
   // bit mask over the dynamic obstacles: 32 bits when the compile-time count allows (64-bit
   // find-first-set / shifts are ~10 instructions each on sm_100)
   using dmask = typename DynMask<(N_ == 0 || ND_ > 32)>::type;
+  static constexpr int kN = N_, kNstc = NS_;
   __device__ __forceinline__ static int mem(const DevCfg &g) { return N_ ? MEM_ : g.mem; }
   __device__ __forceinline__ static int N(const DevCfg &g) { return N_ ? N_ : g.N; }
   __device__ __forceinline__ static int Nother(const DevCfg &g) { return N_ ? NO_ : g.Nother; }
@@ -702,6 +703,30 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
 #ifdef TTMPC_PROFILE
   long long ep_t = clock64();
 #endif
+  // ---- terms of (v, w) alone: speed reference + control action (l.203-204), accelerations and the ALM
+  //      distance (l.250-264).  Formed HERE, ahead of the rollout: the kernel runs two warps per scheduler
+  //      and its top stall is the fixed-latency dependency wait, and the rollout that follows is one long
+  //      chain (theta scan -> sincos -> position scan); in the same basic block these ~60 independent
+  //      instructions fill its bubbles (+3 % solves/s, round 2).  They are ADDED to the cost at their
+  //      original places below, so every accumulation keeps its order and the bits do not change.
+  const double icm = tt_div(1.0, fmax(c, 1.0));  // an out-of-line call: first, so that what follows is ONE block
+  const double vr = sm.vref[lk];
+  double t_vel, t_ctl, t_acc;
+  double aa, aw, ea, ew, alm;
+  {
+    const double dv_ = v - vr;
+    t_vel = cx->qvel * (dv_ * dv_);
+    t_ctl = fma(cx->rw, w * w, cx->rv * (v * v));
+    double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
+    if (lane == 0) { vp = cx->v_init; wp = cx->w_init; }
+    aa = (v - vp) * g.inv_ts; aw = (w - wp) * g.inv_ts;
+    t_acc = fma(aw * aw, cx->wacc_pen, (aa * aa) * cx->acc_pen);
+    double z = fma(ya, icm, aa);
+    ea = z - clipd(z, g.amin, g.amax);
+    z = fma(yw, icm, aw);
+    ew = z - clipd(z, -g.awmax, g.awmax);
+    alm = fma(ew, ew, ea * ea);
+  }
   // ---- rollout (motion_model.py:153-176; RK4 of the unicycle = Simpson in theta):
   //      theta and position are prefix sums over the lanes
   const double tw = ts * w;
@@ -742,6 +767,40 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   double gx = 0.0, gy = 0.0; // d psi / d position_{k+1}
   double S_loc = 0.0, gSx = 0.0, gSy = 0.0;
 
+  // ---- one static obstacle (l.214-220): hard penalty only.  The edge products of an obstacle are formed
+  //      once; its sum / gradient terms are entered through a warp vote by the lanes that are inside it.
+  auto static_obstacle = [&](int i) {
+    const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
+    double m[MAX_EDGE], sq[MAX_EDGE];
+    double inside = 1.0;
+#pragma unroll
+    for (int e = 0; e < MAX_EDGE; e++) {
+      if (e < ne) {
+        m[e] = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
+        sq[e] = m[e] * m[e];
+        inside *= sq[e];
+      }
+    }
+    if (__builtin_expect(__any_sync(FULL, inside > 0.0), 0)) {
+      if (inside > 0.0) {
+        S_loc += inside;
+        if (GRAD) {
+#pragma unroll
+          for (int e = 0; e < MAX_EDGE; e++) {
+            if (e < ne) {
+              double rest = 1.0;
+#pragma unroll
+              for (int e2 = 0; e2 < MAX_EDGE; e2++)
+                if (e2 < ne && e2 != e) rest *= sq[e2];
+              const double coef = rest * (2.0 * m[e]);
+              gSx = fma(coef, na0[e], gSx);
+              gSy = fma(coef, na1[e], gSy);
+            }
+          }
+        }
+      }
+    }
+  };
   // ---- reference-path deviation (l.124-139, 202): min over the remaining segments j >= k.
   //      Step k has N - k segments (lane 0 the most); the 32 - N lanes beyond the horizon take
   //      the upper half of the ranges of the first 32 - N steps, so the loop is ~N/2 long.
@@ -796,12 +855,8 @@ TT_UNROLL_2
   }
   EPROF(1)
   // ---- speed reference + control action (l.203-204)
-  const double vr = sm.vref[lk];
-  {
-    const double dv_ = v - vr;
-    cost += cx->qvel * (dv_ * dv_);
-    cost += fma(cx->rw, w * w, cx->rv * (v * v));
-  }
+  cost += t_vel;
+  cost += t_ctl;
   // ---- fleet collision (l.207-211): contacts are rare -> fp32 prefilter from shared memory,
   //      one vote, then the exact fp64 terms (parameters in global memory) for the flagged
   //      robots in the same order (Nother <= 32)
@@ -940,58 +995,14 @@ TT_UNROLL_2
       gt = 2.0 * cx->qthetaN * dtg;
     }
   }
-  // ---- static obstacles (l.214-220): hard penalty only.  One pass: the edge products of an
-  //      obstacle are formed once; its sum / gradient terms are entered through a warp vote
-  //      (per obstacle) by the lanes that are inside it, in obstacle order like the reference fold.
+  // ---- static obstacles (l.214-220), in obstacle order like the reference fold
   {
 TT_UNROLL_4
-    for (int i = 0; i < Nstc; i++) {
-      const double *b = sm.os + i * nstcobs, *na0 = b + ne, *na1 = b + 2 * ne;
-      double m[MAX_EDGE], sq[MAX_EDGE];
-      double inside = 1.0;
-#pragma unroll
-      for (int e = 0; e < MAX_EDGE; e++) {
-        if (e < ne) {
-          m[e] = relu(fma(na1[e], Y, fma(na0[e], X, b[e])));
-          sq[e] = m[e] * m[e];
-          inside *= sq[e];
-        }
-      }
-      if (__builtin_expect(__any_sync(FULL, inside > 0.0), 0)) {
-        if (inside > 0.0) {
-          S_loc += inside;
-          if (GRAD) {
-#pragma unroll
-            for (int e = 0; e < MAX_EDGE; e++) {
-              if (e < ne) {
-                double rest = 1.0;
-#pragma unroll
-                for (int e2 = 0; e2 < MAX_EDGE; e2++)
-                  if (e2 < ne && e2 != e) rest *= sq[e2];
-                const double coef = rest * (2.0 * m[e]);
-                gSx = fma(coef, na0[e], gSx);
-                gSy = fma(coef, na1[e], gSy);
-              }
-            }
-          }
-        }
-      }
-    }
+    for (int i = 0; i < Nstc; i++) static_obstacle(i);
   }
   EPROF(4)
   // ---- accelerations: cost (l.250-264) and the ALM set C = acc bounds
-  double vp = __shfl_up_sync(FULL, v, 1), wp = __shfl_up_sync(FULL, w, 1);
-  if (lane == 0) { vp = cx->v_init; wp = cx->w_init; }
-  double aa = (v - vp) * g.inv_ts, aw = (w - wp) * g.inv_ts, ea, ew, alm;
-  {
-    cost += fma(aw * aw, cx->wacc_pen, (aa * aa) * cx->acc_pen);
-    const double icm = tt_div(1.0, fmax(c, 1.0));
-    double z = fma(ya, icm, aa);
-    ea = z - clipd(z, g.amin, g.amax);
-    z = fma(yw, icm, aw);
-    ew = z - clipd(z, -g.awmax, g.awmax);
-    alm = fma(ew, ew, ea * ea);
-  }
+  cost += t_acc;
   // ---- lanes beyond the horizon contribute nothing
   if (!act) {
     cost = 0.0; gx = 0.0; gy = 0.0; S_loc = 0.0; gSx = 0.0; gSy = 0.0;
