@@ -632,8 +632,8 @@ static wout_t w_eval(const ttmpc_config *g, const double *p, wstage_t *W, const 
       }
       cost[k] += soft;
     }
-    /* terminal */
-    if (k == N - 1) {
+    /* terminal; the kernel skips the block when both weights are zero (every term is a signed zero then) */
+    if (k == N - 1 && (qN != 0.0 || qthetaN != 0.0)) {
       const double dxg = X[k] - xg, dyg = Y[k] - yg, dtg = TH[k] - thg;
       cost[k] += fma(qthetaN, dtg * dtg, qN * fma(dyg, dyg, dxg * dxg));
       if (GRAD) {

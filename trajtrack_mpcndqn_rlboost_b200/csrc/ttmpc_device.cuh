@@ -70,6 +70,20 @@
 #ifndef TT_FACTOR
 #define TT_FACTOR 4
 #endif
+// Scalar-work switches (round 2, third session; bit-identical either way, tools/r2_ab4.sh / r2_ab5.sh):
+//   1 zero numerators of the envelope divisions bypass the IEEE division (its slow path otherwise)
+//   2 sigma is formed when gamma changes, not in every iteration
+//   4 so is the coefficient of the Lipschitz check (kept in the warp's shared-memory context)
+//   8 the sum over the penalty rows when only the static obstacles contribute is unrolled by 5
+//  16 1 / max(c, 1) is cached per penalty value in the warp's context (eval_psi)
+//  32 the terminal-cost block is skipped when both of its weights are zero (eval_psi; oracle mirrors it)
+// Measured on static4096 (driver protocol): 0 -> 609 k solves/s, 15 -> 661 k (icc hit rate 86.6 -> 90.2 %:
+// the slow path of the division alone was 1.5 KB of hot code), 63 -> 655 k with 9 % fewer executed
+// instructions than 0 (2.22 G against 2.45 G per batch) -- below ~660 k the kernel no longer responds to the
+// instruction count, only to the layout of the hot lines.
+#ifndef TT_OPT
+#define TT_OPT 63
+#endif
 namespace ttmpc {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -214,27 +228,73 @@ __device__ __forceinline__ void down_add(double &v) {  // v += v[lane + O] on la
 #else
 #define TT_SCAN_FN __device__ __forceinline__
 #endif
+// The same scan levels with the offset in a register: a rolled loop of five trips (TT_SCAN_ROLLED, off).
+// One level is the same 9 instructions, the loop adds 3 per trip -- more executed instructions in the scans
+// for 1/4 of their code bytes (the six scans of an evaluation are 3.4 KB unrolled).  Measured (r2_ab5, both
+// scan directions rolled): instruction-cache hit rate 87.7 -> 90.0 %, `no_instruction` 0.65 -> 0.44 per
+// issue, but `wait` 2.14 -> 2.30 and `short_scoreboard` 1.04 -> 1.13: 644-648 k solves/s against 641-667 k.
+__device__ __forceinline__ void up_add_r(double &v, int o) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tl, th;\n\t.reg .f64 t;\n\t"
+               "mov.b64 {lo, hi}, %0;\n\t"
+               "shfl.sync.up.b32 tl|p, lo, %1, 0, 0xffffffff;\n\t"
+               "shfl.sync.up.b32 th, hi, %1, 0, 0xffffffff;\n\t"
+               "mov.b64 t, {tl, th};\n\t"
+               "@p add.rn.f64 %0, %0, t;\n\t}"
+               : "+d"(v) : "r"(o));
+}
+__device__ __forceinline__ void down_add_r(double &v, int o) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tl, th;\n\t.reg .f64 t;\n\t"
+               "mov.b64 {lo, hi}, %0;\n\t"
+               "shfl.sync.down.b32 tl|p, lo, %1, 31, 0xffffffff;\n\t"
+               "shfl.sync.down.b32 th, hi, %1, 31, 0xffffffff;\n\t"
+               "mov.b64 t, {tl, th};\n\t"
+               "@p add.rn.f64 %0, %0, t;\n\t}"
+               : "+d"(v) : "r"(o));
+}
+#ifndef TT_SCAN_ROLLED   // bit 0: prefix scans (rollout)  bit 1: suffix scans (adjoint)
+#define TT_SCAN_ROLLED 0
+#endif
 struct D2 { double a, b; };
 // inclusive prefix sum over lanes (Kogge-Stone)
 TT_SCAN_FN double wscan(double v, int) {
+#if TT_SCAN_ROLLED & 1
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) up_add_r(v, o);
+#else
   up_add<1>(v); up_add<2>(v); up_add<4>(v); up_add<8>(v); up_add<16>(v);
+#endif
   return v;
 }
 TT_SCAN_FN D2 wscan2v(double a, double b) {  // two scans, interleaved
+#if TT_SCAN_ROLLED & 1
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) { up_add_r(a, o); up_add_r(b, o); }
+#else
   up_add<1>(a); up_add<1>(b); up_add<2>(a); up_add<2>(b); up_add<4>(a); up_add<4>(b);
   up_add<8>(a); up_add<8>(b); up_add<16>(a); up_add<16>(b);
+#endif
   D2 r; r.a = a; r.b = b;
   return r;
 }
 __device__ __forceinline__ void wscan2(double &a, double &b) { const D2 r = wscan2v(a, b); a = r.a; b = r.b; }
 // inclusive suffix sum over lanes
 TT_SCAN_FN double wsuffix(double v, int) {
+#if TT_SCAN_ROLLED & 2
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) down_add_r(v, o);
+#else
   down_add<1>(v); down_add<2>(v); down_add<4>(v); down_add<8>(v); down_add<16>(v);
+#endif
   return v;
 }
 TT_SCAN_FN D2 wsuffix2v(double a, double b) {
+#if TT_SCAN_ROLLED & 2
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) { down_add_r(a, o); down_add_r(b, o); }
+#else
   down_add<1>(a); down_add<1>(b); down_add<2>(a); down_add<2>(b); down_add<4>(a); down_add<4>(b);
   down_add<8>(a); down_add<8>(b); down_add<16>(a); down_add<16>(b);
+#endif
   D2 r; r.a = a; r.b = b;
   return r;
 }
@@ -341,6 +401,8 @@ struct WarpCtx {
   double box_half;
   unsigned long long dyn_live;       // bit j: dynamic obstacle j can matter inside the box
   unsigned fleet_live;               // bit j: other robot j can matter inside the box
+  double lipc;                       // PANOC: GAMMA_L_COEFF / (2 gamma) of the current gamma (TT_OPT & 4)
+  double icm_c, icm;                 // 1 / max(c, 1) of the last penalty c this warp evaluated with (TT_OPT & 16)
 #ifdef TTMPC_PROFILE
   long long prof[8];                 // cycles per phase (diagnostic build only)
   long long eprof[10];               // cycles per section of eval_psi
@@ -486,6 +548,7 @@ __device__ inline void stage_part1(const DevCfg &g, const WarpSmem &sm, const do
     c->qvel = q[1]; c->rv = q[3]; c->rw = q[4]; c->qN = q[5]; c->qthetaN = q[6];
     c->qrpd = q[7]; c->acc_pen = q[8]; c->wacc_pen = q[9];
     c->n_cost = 0; c->n_grad = 0; c->n_body = 0;
+    c->lipc = 0.0; c->icm_c = NAN; c->icm = 0.0;  // NaN never compares equal: the first evaluation fills the pair
 #ifdef TTMPC_PROFILE
     for (int i = 0; i < 8; i++) c->prof[i] = 0;
     for (int i = 0; i < 10; i++) c->eprof[i] = 0;
@@ -665,9 +728,21 @@ struct EvalOut {
   double gv, gw;  // this lane's gradient entries (GRAD only)
   // line-search fusion (GRAD and gamma_ls > 0): gradient step s = p - gamma*grad, half step
   // h = proj(s), and the two reduced scalars of the forward-backward envelope
-  double s0, s1, h0, h1, dd, g2;
+  double h0, h1, dd, g2;
   bool any_hard;
 };
+
+// 1 / max(c, 1) for a penalty this warp has not evaluated with yet (see eval_psi); `store` = the calling warp
+// owns the context
+static __device__ __noinline__ double icm_miss(double c, WarpCtx *ctx, bool store) {
+  const double icm = 1.0 / fmax(c, 1.0);
+  if (store) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { ctx->icm = icm; ctx->icm_c = c; }
+    __syncwarp();
+  }
+  return icm;
+}
 
 // Evaluate psi (and its gradient when GRAD) at this lane's (v, w).
 // ya / yw are this lane's multipliers for the linear / angular acceleration rows.
@@ -709,7 +784,17 @@ __device__ __noinline__ EvalOut eval_psi(const DevCfg *gp, unsigned char *smem_b
   //      chain (theta scan -> sincos -> position scan); in the same basic block these ~60 independent
   //      instructions fill its bubbles (+3 % solves/s, round 2).  They are ADDED to the cost at their
   //      original places below, so every accumulation keeps its order and the bits do not change.
+#if TT_OPT & 16
+  // 1 / max(c, 1): c changes once per outer iteration, the division (an out-of-line call, with the NaN-aware
+  // fmax ~55 executed instructions, 4 % of an evaluation) ran in every evaluation.  The warp that owns the
+  // scene keeps the last (c, 1 / max(c, 1)) pair in its context; a helper evaluating on another warp's
+  // tables (Dalt) never touches the pair, so there is one reader / writer and no ordering to think about.
+  // The miss path is a function of its own: inlined it sat in the middle of the hot instruction stream
+  // (0.5 KB the sequential prefetch fetched for nothing: icc hit rate 90.2 -> 87.7 %, -3 % solves/s).
+  const double icm = __builtin_expect(!Dalt && c == cx->icm_c, 1) ? cx->icm : icm_miss(c, sm.ctx, Dalt == nullptr);
+#else
   const double icm = tt_div(1.0, fmax(c, 1.0));  // an out-of-line call: first, so that what follows is ONE block
+#endif
   const double vr = sm.vref[lk];
   double t_vel, t_ctl, t_acc;
   double aa, aw, ea, ew, alm;
@@ -986,7 +1071,13 @@ TT_UNROLL_2
   EPROF(3)
   // ---- terminal cost (l.242)
   double gt = 0.0;
+#if TT_OPT & 32
+  // both terminal weights zero (config/mpc_default.yaml): every term below is a signed zero; the block is
+  // a divergent branch of ~25 instructions run by one lane while 31 wait.  Mirrored in the oracle's WARP order.
+  if (lane == N - 1 && (cx->qN != 0.0 || cx->qthetaN != 0.0)) {
+#else
   if (lane == N - 1) {
+#endif
     const double dxg = X - cx->xg, dyg = Y - cx->yg, dtg = TH - cx->thg;
     cost += fma(cx->qthetaN, dtg * dtg, cx->qN * fma(dyg, dyg, dxg * dxg));
     if (GRAD) {
@@ -1021,7 +1112,13 @@ TT_UNROLL_4
       sumF2 += F2j;
     }
   } else if (__builtin_expect(S != 0.0, 0)) {  // every D_j is zero: F2_j = S + 0.0 = S (same operations, no loads)
+    // taken by every second evaluation of the static workload (a robot inside a polygon): two dependent
+    // chains of Ndyn links; unrolled by 5 the 15 trips cost 39 instructions instead of 75
+#if TT_OPT & 8
+#pragma unroll 5
+#else
 #pragma unroll 1
+#endif
     for (int j = 0; j < Ndyn; j++) {
       f2sq = fma(S, S, f2sq);
       sumF2 += S;
@@ -1030,7 +1127,7 @@ TT_UNROLL_4
   EvalOut out;
   out.f2sq = f2sq; out.S = S; out.any_hard = any_hard;
   out.gv = 0.0; out.gw = 0.0;
-  out.s0 = out.s1 = out.h0 = out.h1 = out.dd = out.g2 = 0.0;
+  out.h0 = out.h1 = out.dd = out.g2 = 0.0;
   double ddp = 0.0, g2p = 0.0;
 
   EPROF(6)
@@ -1083,9 +1180,9 @@ TT_UNROLL_4
     }
     out.gv = gv; out.gw = gw;
     if (gamma_ls > 0.0 && act) {  // PANOC line search: gradient step, projection, envelope terms
-      out.s0 = fma(-gamma_ls, gv, v); out.s1 = fma(-gamma_ls, gw, w);
-      out.h0 = clipd(out.s0, g.vmin, g.vmax); out.h1 = clipd(out.s1, -g.wmax, g.wmax);
-      const double q0 = out.h0 - out.s0, q1 = out.h1 - out.s1;
+      const double s0 = fma(-gamma_ls, gv, v), s1 = fma(-gamma_ls, gw, w);
+      out.h0 = clipd(s0, g.vmin, g.vmax); out.h1 = clipd(s1, -g.wmax, g.wmax);
+      const double q0 = out.h0 - s0, q1 = out.h1 - s1;
       ddp = pdot(q0, q1, q0, q1);
       g2p = pdot(gv, gw, gv, gw);
     }

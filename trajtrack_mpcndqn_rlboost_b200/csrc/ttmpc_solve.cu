@@ -61,7 +61,6 @@ struct Lane {
   double g0, g1;          // gradient at u (or u_plus during the line search)
   double gp0, gp1;        // previous gradient (AKKT residual)
   double h0, h1;          // u_half_step
-  double s0, s1;          // gradient_step
   double d0, d1;          // L-BFGS direction
   double f0, f1;          // gamma * fixed point residual
   double os0, os1, og0, og1;  // lbfgs old_state / old_g
@@ -70,14 +69,50 @@ struct Lane {
 struct Uni {  // warp-uniform scalars
   double gamma, L, sigma, cost, norm_fpr, tau, akkt_tol, lb_gamma;
   double ip;              // <grad, fpr>, reduced together with |fpr|^2
-  double env_dd, env_g2;  // |gstep - u_half|^2 and |grad|^2 at the current iterate, as
-  int env_valid;          // returned by the accepted line-search evaluation
+  double env_dd, env_g2;  // |gstep - u_half|^2 and |grad|^2 of the current gradient step / half step: from the
+                          // accepted line-search evaluation, or formed where the solver takes the step itself
   int iteration, lb_active, lb_head, lb_first;
 };
 
 __device__ __forceinline__ void project(const DevCfg &g, double a0, double a1, double &o0, double &o1) {
   o0 = clipd(a0, g.vmin, g.vmax);
   o1 = clipd(a1, -g.wmax, g.wmax);
+}
+
+// The two scalars PANOC derives from gamma alone.  OpEn recomputes them in every iteration from an
+// unchanged gamma (update_lipschitz_constant: the right-hand side of the check and sigma); a division
+// is a 22-instruction call, so they are formed where gamma changes -- same operands, same IEEE
+// division, same bits.
+// (The coefficient of the check lives in the warp's shared-memory context: a 256th register does
+// not exist and a spill costs more than the broadcast load.)
+__device__ __forceinline__ void set_lip_coeff(const Uni &U, const WarpSmem &sm) {
+#if TT_OPT & 4
+  const double lc = tt_div(GAMMA_L_COEFF, 2.0 * U.gamma);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) sm.ctx->lipc = lc;
+  __syncwarp();
+#endif
+}
+__device__ __forceinline__ void set_gamma_terms(Uni &U, const WarpSmem &sm) {
+  U.sigma = tt_div(1.0 - GAMMA_L_COEFF, 4.0 * U.gamma);
+  set_lip_coeff(U, sm);
+}
+__device__ __forceinline__ double lip_coeff(const Uni &U, const WarpSmem &sm) {
+#if TT_OPT & 4
+  return sm.ctx->lipc;
+#else
+  return tt_div(GAMMA_L_COEFF, 2.0 * U.gamma);
+#endif
+}
+// x / gamma for the forward-backward envelope.  x = |gradient step - half step|^2 / 2 is exactly zero
+// whenever no box bound is active, and a zero numerator sends the IEEE division down its slow path
+// (~60 instructions and 1.5 KB of otherwise cold code in the instruction cache, taken by 11 % of all
+// divisions of a static4096 batch).  0 / y = 0 with the sign of x for every y > 0: same bits.
+__device__ __forceinline__ double div_env(double x, double y) {
+#if TT_OPT & 1
+  if (x == 0.0 && y > 0.0) return x;
+#endif
+  return tt_div(x, y);
 }
 
 // ---------------------------------------------------------------- L-BFGS, two-loop recursion
@@ -305,7 +340,7 @@ __device__ __forceinline__ bool help_wait(HelpCtl &hc, const WarpSmem &sm, int l
     e.gw = lane < N ? hr[2 * lane + 1] : 0.0;
   }
   e.any_hard = false;
-  e.s0 = e.s1 = e.h0 = e.h1 = 0.0;
+  e.h0 = e.h1 = 0.0;
   __syncwarp();
   if (!SP && lane == 0) *reinterpret_cast<volatile int *>(&sm.hhdr->state) = 0;
   return true;
@@ -322,7 +357,7 @@ __device__ __forceinline__ EvalOut remote_eval(HelpCtl &hc, const WarpSmem &sm, 
   help_post<true>(hc, sm, lane, N, v, w, c, grad, gamma_ls, CMD_EVAL, 0, st_out);
   if (!help_wait<true>(hc, sm, lane, N, e)) {
     e.psi = e.f = e.f2sq = e.S = e.dd = e.g2 = e.gv = e.gw = NAN;
-    e.s0 = e.s1 = e.h0 = e.h1 = NAN; e.any_hard = false;
+    e.h0 = e.h1 = NAN; e.any_hard = false;
   }
   return e;
 }
@@ -384,10 +419,19 @@ __device__ __forceinline__ void compute_fpr(Lane &z, Uni &U) {
   U.norm_fpr = tt_sqrt(nf);
   U.ip = ip;
 }
-__device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z, const Uni &U,
+// The gradient step s = a - gamma g lives only here and in eval_psi: nothing reads it later except the two
+// envelope scalars, which are formed right away where the solver needs them (ENV).
+template <bool ENV>
+__device__ __forceinline__ void gradient_and_half_step(const DevCfg &g, Lane &z, Uni &U,
                                                        double a0, double a1) {
-  z.s0 = fma(-U.gamma, z.g0, a0); z.s1 = fma(-U.gamma, z.g1, a1);
-  project(g, z.s0, z.s1, z.h0, z.h1);
+  const double s0 = fma(-U.gamma, z.g0, a0), s1 = fma(-U.gamma, z.g1, a1);
+  project(g, s0, s1, z.h0, z.h1);
+  if constexpr (ENV) {
+    const double e0 = s0 - z.h0, e1 = s1 - z.h1;
+    double dist2 = pdot(e0, e1, e0, e1), gg = pdot(z.g0, z.g1, z.g0, z.g1);
+    wsum2(dist2, gg);
+    U.env_dd = dist2; U.env_g2 = gg;
+  }
 }
 
 // Serve owner m (helper slot already taken) until its current scene ends.
@@ -581,7 +625,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       if (!got) cost_half = eval_cost<DM, SP>(g, sm, lane, pb, z.h0, z.h1, hc);
       if (spec) {
         const double rhs0 = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
-                            tt_div(GAMMA_L_COEFF, 2.0 * U.gamma) * (U.norm_fpr * U.norm_fpr);
+                            lip_coeff(U, sm) * (U.norm_fpr * U.norm_fpr);
         if (cost_half > rhs0 && U.L < MAX_LIPSCHITZ_CONSTANT) {  // speculation lost
           U.lb_first = s_first; U.lb_head = s_head; U.lb_active = s_active; U.lb_gamma = s_gamma;
           z.os0 = s_os0; z.os1 = s_os1; z.og0 = s_og0; z.og1 = s_og1;
@@ -592,39 +636,37 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       int it = 0;
       while (true) {
         const double rhs = U.cost + LIPSCHITZ_UPDATE_EPSILON * fabs(U.cost) - U.ip +
-                           tt_div(GAMMA_L_COEFF, 2.0 * U.gamma) * (U.norm_fpr * U.norm_fpr);
+                           lip_coeff(U, sm) * (U.norm_fpr * U.norm_fpr);
         if (!(cost_half > rhs && it < MAX_LIPSCHITZ_UPDATE_ITERATIONS &&
               U.L < MAX_LIPSCHITZ_CONSTANT))
           break;
         U.lb_active = 0; U.lb_first = 1;  // lbfgs.reset()
-        U.env_valid = 0;                  // gamma changes: gradient step and half step move
         U.L *= 2.0;
         U.gamma /= 2.0;
-        gradient_and_half_step(g, z, U, z.u0, z.u1);
+        set_lip_coeff(U, sm);
+        gradient_and_half_step<false>(g, z, U, z.u0, z.u1);
         cost_half = eval_cost<DM, SP>(g, sm, lane, pb, z.h0, z.h1, hc);
         compute_fpr(z, U);
         it++;
       }
+      // gamma moved: the envelope scalars of the new gradient step / half step (iteration 0 takes its own step below)
+      if (it > 0 && U.iteration > 0) gradient_and_half_step<true>(g, z, U, z.u0, z.u1);
+#if TT_OPT & 2
+      if (it > 0) U.sigma = tt_div(1.0 - GAMMA_L_COEFF, 4.0 * U.gamma);  // gamma moved
+#else
       U.sigma = tt_div(1.0 - GAMMA_L_COEFF, 4.0 * U.gamma);
+#endif
     }
   }
   if (U.iteration == 0) {
     // update_no_linesearch
     z.u0 = z.h0; z.u1 = z.h1;
     U.cost = eval_grad<DM, SP>(g, sm, lane, pb, z.u0, z.u1, z.g0, z.g1, hc);
-    gradient_and_half_step(g, z, U, z.u0, z.u1);
-    U.env_valid = 0;
+    gradient_and_half_step<true>(g, z, U, z.u0, z.u1);
   } else {
     // linesearch on the forward-backward envelope
-    double dist2, gg;
-    if (U.env_valid) {  // same vectors as in the evaluation that produced this iterate
-      dist2 = U.env_dd; gg = U.env_g2;
-    } else {
-      const double e0 = z.s0 - z.h0, e1 = z.s1 - z.h1;
-      dist2 = pdot(e0, e1, e0, e1); gg = pdot(z.g0, z.g1, z.g0, z.g1);
-      wsum2(dist2, gg);
-    }
-    const double fbe = U.cost - 0.5 * U.gamma * gg + tt_div(0.5 * dist2, U.gamma);
+    const double dist2 = U.env_dd, gg = U.env_g2;  // same vectors as in the evaluation / step that produced this iterate
+    const double fbe = U.cost - 0.5 * U.gamma * gg + div_env(0.5 * dist2, U.gamma);
     const double rhs_ls = fbe - U.sigma * (U.norm_fpr * U.norm_fpr);
     U.tau = 1.0;
     int nls = 0;
@@ -642,9 +684,9 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         if (lane == 0) sm.ctx->n_grad++;
         U.cost = e.psi;
         z.g0 = e.gv; z.g1 = e.gw;
-        gradient_and_half_step(g, z, U, p0, p1);
-        const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + tt_div(0.5 * e.dd, U.gamma);
-        U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
+        gradient_and_half_step<false>(g, z, U, p0, p1);
+        const double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + div_env(0.5 * e.dd, U.gamma);
+        U.env_dd = e.dd; U.env_g2 = e.g2;
         if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
         U.tau /= 2.0;
         nls++;
@@ -666,9 +708,9 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
       PROF_END(t0, 1)
       if (lane == 0) sm.ctx->n_grad++;
       U.cost = e.psi;
-      z.g0 = e.gv; z.g1 = e.gw; z.s0 = e.s0; z.s1 = e.s1; z.h0 = e.h0; z.h1 = e.h1;
-      double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + tt_div(0.5 * e.dd, U.gamma);
-      U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
+      z.g0 = e.gv; z.g1 = e.gw; z.h0 = e.h0; z.h1 = e.h1;
+      double lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + div_env(0.5 * e.dd, U.gamma);
+      U.env_dd = e.dd; U.env_g2 = e.g2;
       if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
       U.tau /= 2.0;
       nls++;
@@ -677,9 +719,9 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
         p0 = n0; p1 = n1;
         U.cost = e.psi;
         z.g0 = e.gv; z.g1 = e.gw;
-        gradient_and_half_step(g, z, U, p0, p1);  // same s = p - gamma g, h = proj(s) the evaluation formed
-        lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + tt_div(0.5 * e.dd, U.gamma);
-        U.env_dd = e.dd; U.env_g2 = e.g2; U.env_valid = 1;
+        gradient_and_half_step<false>(g, z, U, p0, p1);  // same s = p - gamma g, h = proj(s) the evaluation formed
+        lhs_ls = U.cost - 0.5 * U.gamma * e.g2 + div_env(0.5 * e.dd, U.gamma);
+        U.env_dd = e.dd; U.env_g2 = e.g2;
         if (!(lhs_ls > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
         U.tau /= 2.0;
         nls++;
@@ -694,7 +736,7 @@ __device__ __forceinline__ bool panoc_step(const DevCfg &g, const WarpSmem &sm, 
 }
 
 __device__ __forceinline__ void panoc_reset(Uni &U) {
-  U.lb_active = 0; U.lb_first = 1; U.env_valid = 0;
+  U.lb_active = 0; U.lb_first = 1; U.env_dd = 0.0; U.env_g2 = 0.0;
   U.tau = 1.0; U.L = 0.0; U.sigma = 0.0; U.cost = 0.0; U.iteration = 0; U.gamma = 0.0;
 }
 
@@ -724,7 +766,7 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
     }
   }
   pb.c = A.c0 ? A.c0[scene] : g.c0;
-  z.g0 = z.g1 = z.gp0 = z.gp1 = z.h0 = z.h1 = z.s0 = z.s1 = 0.0;
+  z.g0 = z.g1 = z.gp0 = z.gp1 = z.h0 = z.h1 = 0.0;
   z.d0 = z.d1 = z.f0 = z.f1 = z.os0 = z.os1 = z.og0 = z.og1 = 0.0;
   U.lb_head = 0; U.lb_gamma = 1.0; U.norm_fpr = 0.0;
   panoc_reset(U);
@@ -772,8 +814,8 @@ __device__ void solve_scene(const DevCfg &g, const WarpSmem &sm, const SolveArgs
         U.L = sqrt(nd) / sqrt(nh);
       }
       U.gamma = GAMMA_L_COEFF / fmax(U.L, MIN_L_ESTIMATE);
-      U.sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * U.gamma);
-      gradient_and_half_step(g, z, U, z.u0, z.u1);
+      set_gamma_terms(U, sm);
+      gradient_and_half_step<false>(g, z, U, z.u0, z.u1);
 
       // PANOCOptimizer::solve main loop (one call site: step, then count)
       int num_iter = 0;
