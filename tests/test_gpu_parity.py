@@ -75,6 +75,25 @@ def test_solve_parity_with_oracle(cfg, solver, n_static, n_dynamic, seed):
     assert_parity(sol, ref, n)
 
 
+def test_solve_parity_with_terminal_weights_and_changing_penalties(cfg, solver):
+    """mpc_default.yaml has both terminal weights at zero and the kernel skips the terminal-cost block then; with
+    non-zero weights (and an initial penalty below 1, so that 1 / max(c, 1) stays at 1 over the first outer
+    iterations while c changes) the solve must still be the oracle's, bit for bit."""
+    from trajtrack_mpcndqn_rlboost_b200.mpc_config import param_offsets
+    n = 128
+    p = t.scenes.make_scenes(n, cfg, seed=21, n_static=4, n_dynamic=3, blocking_fraction=0.2)
+    off = param_offsets(cfg)
+    p[:, off["q"] + 5] = 2.0   # qpN
+    p[:, off["q"] + 6] = 1.5   # qthetaN
+    sol = solver.run(p)
+    ref = O.solve_batch(cfg, p, threads=os.cpu_count(), warp=True)
+    assert_parity(sol, ref, n)
+    c0 = np.full(n, 0.3)
+    sol = solver.run(p, initial_penalty=c0)
+    ref = O.solve_batch(cfg, p, c0=c0, threads=os.cpu_count(), warp=True)
+    assert_parity(sol, ref, n)
+
+
 def test_split_kernel_parity_with_oracle(cfg, solver, monkeypatch):
     """The experimental cluster kernel (solver CTA + evaluator CTA over DSMEM, TTMPC_SPLIT=1)
     must produce the same bits as the default kernel and the oracle."""
