@@ -77,12 +77,14 @@
 //   8 the sum over the penalty rows when only the static obstacles contribute is unrolled by 5
 //  16 1 / max(c, 1) is cached per penalty value in the warp's context (eval_psi)
 //  32 the terminal-cost block is skipped when both of its weights are zero (eval_psi; oracle mirrors it)
+//  64 the butterflies of the L-BFGS two-loop recursion are inlined (ttmpc_solve.cu lbfgs_apply)
 // Measured on static4096 (driver protocol): 0 -> 609 k solves/s, 15 -> 661 k (icc hit rate 86.6 -> 90.2 %:
 // the slow path of the division alone was 1.5 KB of hot code), 63 -> 655 k with 9 % fewer executed
 // instructions than 0 (2.22 G against 2.45 G per batch) -- below ~660 k the kernel no longer responds to the
-// instruction count, only to the layout of the hot lines.
+// instruction count, only to the layout of the hot lines and to the length of the dependent chain of an
+// iteration (127: 658.5 -> 666.7 k).
 #ifndef TT_OPT
-#define TT_OPT 63
+#define TT_OPT 127
 #endif
 namespace ttmpc {
 

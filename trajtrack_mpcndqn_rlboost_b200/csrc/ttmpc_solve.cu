@@ -162,6 +162,15 @@ __device__ __forceinline__ void lbfgs_update(const DevCfg &g, const WarpSmem &sm
   __syncwarp();
 }
 
+// The 2 m inner products of the recursion are one dependent chain (each needs the vector the previous one
+// left), and with two warps per scheduler the solve follows the length of its dependent chains: their
+// butterfly is inlined (TT_OPT & 64: no call, no argument / result moves on that chain) at the price of
+// ~0.5 KB of hot code.  658.5 -> 666.7 k solves/s (two interleaved runs each, tools/r2_ab5.sh ab11).
+#if TT_OPT & 64
+#define TT_LBFGS_WSUM wsum_inl
+#else
+#define TT_LBFGS_WSUM wsum
+#endif
 // lbfgs::apply_hessian on the direction
 template <class DM>
 __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm, Lane &z,
@@ -176,7 +185,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
 #pragma unroll 1
   for (int i = 0; i < m; i++) {  // newest to oldest
     const double2 s = sm.lbs[k * NP + lk], y = sm.lby[k * NP + lk];
-    const double a = sm.rho[k] * wsum(act ? pdot(s.x, s.y, q0, q1) : 0.0);
+    const double a = sm.rho[k] * TT_LBFGS_WSUM(act ? pdot(s.x, s.y, q0, q1) : 0.0);
     if (lane == i) a_me = a;
     q0 = fma(-a, y.x, q0); q1 = fma(-a, y.y, q1);
     k = (k + 1 == M1) ? 0 : k + 1;
@@ -186,7 +195,7 @@ __device__ __forceinline__ void lbfgs_apply(const DevCfg &g, const WarpSmem &sm,
   for (int i = m - 1; i >= 0; i--) {  // oldest to newest
     k = (k == 0) ? M1 - 1 : k - 1;
     const double2 s = sm.lbs[k * NP + lk], y = sm.lby[k * NP + lk];
-    const double beta = sm.rho[k] * wsum(act ? pdot(y.x, y.y, q0, q1) : 0.0);
+    const double beta = sm.rho[k] * TT_LBFGS_WSUM(act ? pdot(y.x, y.y, q0, q1) : 0.0);
     const double cf = __shfl_sync(FULL, a_me, i) - beta;
     q0 = fma(cf, s.x, q0); q1 = fma(cf, s.y, q1);
   }
