@@ -9,7 +9,14 @@
  *         PANOC (panoc_engine.rs / panoc_cache.rs / panoc_optimizer.rs),
  *         L-BFGS with C-BFGS safeguard (lbfgs crate), ALM/PM outer loop
  *         (alm_optimizer.rs), local Lipschitz estimate (lipschitz_estimator.rs).
- *         PARITY UNPINNED: restated from the published algorithm.
+ *         PARITY UNPINNED: restated from the published algorithm; no output of the real solver on
+ *         this problem exists here.  Anchored (round 2) on the known answers the two crates' OWN unit
+ *         tests hold, restated with their test problems: the lbfgs crate's correctneess_buff_1
+ *         direction (to 1e-14), the fixed points mocks::SOLUTION_A / SOLUTION_HARD that PANOC must
+ *         reach on mocks::my_cost / hard_quadratic_cost over a Euclidean ball, the local Lipschitz
+ *         estimate of mocks::lipschitz_mock (tests/test_oracle_solver.py; every constant is also
+ *         checked against what it must satisfy -- hand arithmetic, KKT conditions).  These pin the
+ *         building blocks and the fixed points, not the iterate path on the NMPC problem.
  */
 #include "ttmpc_oracle.h"
 
@@ -769,15 +776,52 @@ typedef struct {
   long long n_cost, n_grad;
   int warp;        /* 0: reference order (Part 1, libm)  1: GPU order (Part 1b) */
   wstage_t *W;
+  int mock;        /* 0: the NMPC problem; 1, 2: the crate's own unit-test problems (see ttmpc_oracle_panoc_mock) */
 } prob_t;
 
+/* The two test problems of optimization_engine's src/mocks.rs (my_cost / my_gradient over a Euclidean ball of
+ * radius 0.2, hard_quadratic_cost / hard_quadratic_gradient over a ball of radius 0.05), restated from the crate;
+ * the crate's unit tests (t_panoc_basic and friends) assert that PANOC reaches mocks::SOLUTION_A / SOLUTION_HARD
+ * on them.  tests/test_oracle_solver.py runs the PANOC engine below on both and checks the constants (and,
+ * independently of anybody's memory of them, the KKT conditions of the two problems at the point reached). */
+static double mock_cost(int which, const double *u) {
+  if (which == 3) return 0.0;
+  if (which == 1)
+    return 0.5 * (u[0] * u[0] + 2. * u[1] * u[1] + 2.0 * u[0] * u[1]) + u[0] - u[1] + 3.0;
+  return (4. * u[0] * u[0]) / 2. + 5.5 * u[1] * u[1] + 500.5 * u[2] * u[2] + 5. * u[0] * u[1] +
+         25. * u[0] * u[2] + 5. * u[1] * u[2] + u[0] + u[1] + u[2];
+}
+static void mock_grad(int which, const double *u, double *g) {
+  if (which == 3) { /* mocks::lipschitz_mock */
+    g[0] = 3.0 * u[0]; g[1] = 2.0 * u[1]; g[2] = 4.5;
+  } else if (which == 1) {
+    g[0] = u[0] + u[1] + 1.0;
+    g[1] = u[0] + 2. * u[1] - 1.0;
+  } else {
+    g[0] = 4. * u[0] + 5. * u[1] + 25. * u[2] + 1.;
+    g[1] = 5. * u[0] + 11. * u[1] + 5. * u[2] + 1.;
+    g[2] = 25. * u[0] + 5. * u[1] + 1001. * u[2] + 1.;
+  }
+}
+/* constraints::Ball2::new(None, r).project */
+static void mock_project(int which, double *u) {
+  const int n = which == 1 ? 2 : 3;
+  const double r = which == 1 ? 0.2 : 0.05;
+  double nrm = 0.0;
+  for (int i = 0; i < n; i++) nrm += u[i] * u[i];
+  nrm = sqrt(nrm);
+  if (nrm > r) for (int i = 0; i < n; i++) u[i] *= r / nrm;
+}
+
 static void f_cost(prob_t *pb, const double *u, double *out) {
-  if (pb->warp) *out = w_eval(pb->g, pb->p, pb->W, u, pb->c, pb->y, NULL, NULL).psi;
+  if (pb->mock) *out = mock_cost(pb->mock, u);
+  else if (pb->warp) *out = w_eval(pb->g, pb->p, pb->W, u, pb->c, pb->y, NULL, NULL).psi;
   else *out = ttmpc_oracle_psi(pb->g, u, pb->p, pb->c, pb->y);
   pb->n_cost++;
 }
 static void f_grad(prob_t *pb, const double *u, double *out) {
-  if (pb->warp) w_eval(pb->g, pb->p, pb->W, u, pb->c, pb->y, out, NULL);
+  if (pb->mock) mock_grad(pb->mock, u, out);
+  else if (pb->warp) w_eval(pb->g, pb->p, pb->W, u, pb->c, pb->y, out, NULL);
   else ttmpc_oracle_psi_grad(pb->g, u, pb->p, pb->c, pb->y, out);
   pb->n_grad++;
 }
@@ -920,9 +964,10 @@ static int pc_exit(const panoc_t *c) {
 static void pe_gradient_step(panoc_t *c, const double *u) {
   for (int i = 0; i < c->n; i++) c->gstep[i] = mad(-c->gamma, c->grad[i], u[i]);
 }
-static void pe_half_step(panoc_t *c, const ttmpc_config *g) {
+static void pe_half_step(panoc_t *c, const prob_t *pb) {
   memcpy(c->u_half, c->gstep, c->n * sizeof(double));
-  project_u(g, c->u_half);
+  if (pb->mock) mock_project(pb->mock, c->u_half);
+  else project_u(pb->g, c->u_half);
 }
 static void pe_fpr(panoc_t *c, const double *u) {
   for (int i = 0; i < c->n; i++) c->fpr[i] = u[i] - c->u_half[i];
@@ -934,7 +979,7 @@ static void pe_init(panoc_t *c, prob_t *pb, double *u) {
   f_cost(pb, u, &c->cost);
   /* LipschitzEstimator: h_i = max(delta, eps*u_i); L = |grad(u+h)-grad(u)|/|h| */
   {
-    double h[MAXNU], up[MAXNU], g2[MAXNU];
+    double h[MAXNU] = {0.0}, up[MAXNU], g2[MAXNU];
     f_grad(pb, u, c->grad);
     for (int i = 0; i < n; i++) {
       h[i] = (EPSILON_LIPSCHITZ * u[i] > DELTA_LIPSCHITZ) ? EPSILON_LIPSCHITZ * u[i]
@@ -948,7 +993,7 @@ static void pe_init(panoc_t *c, prob_t *pb, double *u) {
   c->gamma = GAMMA_L_COEFF / fmax(c->L, MIN_L_ESTIMATE);
   c->sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * c->gamma);
   pe_gradient_step(c, u);
-  pe_half_step(c, pb->g);
+  pe_half_step(c, pb);
 }
 static double pe_lip_rhs(panoc_t *c) {
   double ip = dot(c->n, c->grad, c->fpr);
@@ -966,7 +1011,7 @@ static void pe_update_lipschitz(panoc_t *c, prob_t *pb, const double *u) {
     c->L *= 2.0;
     c->gamma /= 2.0;
     pe_gradient_step(c, u);
-    pe_half_step(c, pb->g);
+    pe_half_step(c, pb);
     f_cost(pb, c->u_half, &cost_half);
     pe_fpr(c, u);
     it++;
@@ -980,7 +1025,7 @@ static int pe_ls_condition(panoc_t *c, prob_t *pb, const double *u) {
   f_cost(pb, c->u_plus, &c->cost);
   f_grad(pb, c->u_plus, c->grad);
   for (int i = 0; i < n; i++) c->gstep[i] = mad(-c->gamma, c->grad[i], c->u_plus[i]);
-  pe_half_step(c, pb->g);
+  pe_half_step(c, pb);
   const double dd = norm2sq_diff(n, c->u_half, c->gstep), g2 = dot(n, c->grad, c->grad);
   c->lhs_ls = c->cost - 0.5 * c->gamma * g2 + 0.5 * dd / c->gamma;
   return c->lhs_ls > c->rhs_ls;
@@ -1004,7 +1049,7 @@ static int pe_step(panoc_t *c, prob_t *pb, double *u) {
     f_cost(pb, u, &c->cost);
     f_grad(pb, u, c->grad);
     pe_gradient_step(c, u);
-    pe_half_step(c, pb->g);
+    pe_half_step(c, pb);
   } else {
     /* linesearch */
     const double dist2 = norm2sq_diff(n, c->gstep, c->u_half), gg = dot(n, c->grad, c->grad);
@@ -1039,12 +1084,76 @@ static int panoc_solve(panoc_t *c, prob_t *pb, double *u, int max_iter, int *ite
   return cont_iters ? TTMPC_CONVERGED : TTMPC_NOT_CONVERGED_ITERATIONS;
 }
 
+/* The L-BFGS restatement on a caller-supplied history: n_updates calls of update_hessian(g_i, x_i) (the first
+ * one only stores the point, like in the crate), then apply_hessian(q).  cbfgs = 0: Lbfgs::new defaults (no
+ * C-BFGS test), 1: the settings PANOCCache::new chooses.  tests/test_oracle_solver.py checks the known answer of
+ * the lbfgs crate's own unit test (correctneess_buff_1) with it.  alpha0 / rho0 = alpha and rho of the newest pair. */
+int ttmpc_oracle_lbfgs_kat(int n, int mem, int n_updates, const double *g, const double *x, double *q,
+                           double *alpha0, double *rho0, int cbfgs) {
+  if (n < 1 || n > MAXNU || mem < 1 || mem > MAXMEM) return -1;
+  lbfgs_t *l = (lbfgs_t *)calloc(1, sizeof(lbfgs_t));
+  g_warp_mode = 0;
+  lb_init(l, n, mem);
+  if (!cbfgs) { l->cbfgs_alpha = 0.0; l->cbfgs_eps = 0.0; }
+  int accepted = 0;
+  for (int i = 0; i < n_updates; i++)
+    accepted += lb_update(l, g + (size_t)i * n, x + (size_t)i * n, norm2(n, g + (size_t)i * n));
+  lb_apply(l, q);
+  if (alpha0) *alpha0 = l->alpha[0];
+  if (rho0) *rho0 = l->rho[lb_idx(l, 0)];
+  const int active = l->active;
+  free(l);
+  return 100 * accepted + active;
+}
+
+/* PANOCEngine::init's local Lipschitz estimate (LipschitzEstimator with PANOC's delta = 1e-12, epsilon = 1e-6) of
+ * mocks::lipschitz_mock at u[3]; the crate's t_test_lip_estimator_mock expects 1.336306209562 at (1, 2, 3). */
+double ttmpc_oracle_lipschitz_mock(const double *u3) {
+  panoc_t *pc = (panoc_t *)calloc(1, sizeof(panoc_t));
+  prob_t pb = {NULL, NULL, 0.0, NULL, 0, 0, 0, NULL, 3};
+  double u[3] = {u3[0], u3[1], u3[2]};
+  g_warp_mode = 0;
+  pc->n = 3;
+  lb_init(&pc->lb, 3, 3);
+  pc_reset(pc);
+  pc->akkt_tol = INFINITY;
+  pe_init(pc, &pb, u);
+  const double L = pc->L;
+  free(pc);
+  return L;
+}
+
+/* PANOCOptimizer::solve on one of the crate's unit-test problems (which = 1: my_cost, 2 variables, ball 0.2;
+ * which = 2: hard_quadratic_cost, 3 variables, ball 0.05), reference operation order, no AKKT test (a plain
+ * PANOCCache has none).  Returns the exit status; u in/out. */
+int ttmpc_oracle_panoc_mock(int which, double *u, double tolerance, int lbfgs_memory, int max_iter,
+                            int *iters, double *norm_fpr, long long *n_cost, long long *n_grad) {
+  if (which != 1 && which != 2) return -1;
+  if (lbfgs_memory < 1 || lbfgs_memory > MAXMEM) return -1;
+  panoc_t *pc = (panoc_t *)calloc(1, sizeof(panoc_t));
+  prob_t pb = {NULL, NULL, 0.0, NULL, 0, 0, 0, NULL, which};
+  g_warp_mode = 0;
+  pc->n = which == 1 ? 2 : 3;
+  lb_init(&pc->lb, pc->n, lbfgs_memory);
+  pc->tolerance = tolerance;
+  pc_reset(pc);
+  pc->akkt_tol = INFINITY; /* akkt_tolerance: None */
+  int it = 0;
+  const int st = panoc_solve(pc, &pb, u, max_iter, &it);
+  if (iters) *iters = it;
+  if (norm_fpr) *norm_fpr = pc->norm_fpr;
+  if (n_cost) *n_cost = pb.n_cost;
+  if (n_grad) *n_grad = pb.n_grad;
+  free(pc);
+  return st;
+}
+
 /* ---- ALM / PM outer loop (alm_optimizer.rs) ---- */
 static int solve_mode(const ttmpc_config *g, const double *p, double *u, double *y, double c0,
                       ttmpc_oracle_status *st, int warp) {
   const int N = g->N_hor, n = 2 * N, n1 = 2 * N, n2 = g->Ndynobs;
   panoc_t *pc = (panoc_t *)calloc(1, sizeof(panoc_t));
-  prob_t pb = {g, p, c0, y, 0, 0, warp, NULL};
+  prob_t pb = {g, p, c0, y, 0, 0, warp, NULL, 0};
   double y_plus[MAXNU], w1[MAXNU], w2[MAXDYN];
   double delta_y_norm = 0.0, delta_y_norm_plus = 0.0, f2_norm = 0.0, f2_norm_plus = 0.0;
   double last_fpr = 0.0, f_final = 0.0;

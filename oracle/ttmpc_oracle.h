@@ -15,8 +15,14 @@
  *     requirements.txt:25; crate 0.7.x, lbfgs 0.2.x), absent from
  *     /root/reference and not buildable here (no Rust).  Restated from the
  *     published algorithm (Stella et al. 2017; Sopasakis et al. 2020) and the
- *     crate's documented constants.
- *   sector/ray observation: PARITY UNPINNED (shapely absent); Q-network: PINNED
+ *     crate's documented constants.  Anchored on the known answers of the two
+ *     crates' own unit tests (lbfgs correctneess_buff_1; PANOC's fixed points
+ *     mocks::SOLUTION_A / SOLUTION_HARD; the Lipschitz estimate of
+ *     mocks::lipschitz_mock): ttmpc_oracle_lbfgs_kat / _panoc_mock /
+ *     _lipschitz_mock below, tests/test_oracle_solver.py.  Building blocks and
+ *     fixed points only -- the iterate path on the NMPC problem is unpinned.
+ *   sector/ray observation: PARITY UNPINNED (shapely absent; checked by an
+ *     independent method, tests/test_geometry_independent.py); Q-network: PINNED
  *     against torch with the reference's Model/ray/best_model.zip weights.
  */
 #ifndef TTMPC_ORACLE_H
@@ -60,6 +66,15 @@ void ttmpc_oracle_eval_warp(const ttmpc_config *cfg, const double *u, const doub
                             double c, const double *y, double *f, double *F2,
                             double *psi, double *grad);
 void ttmpc_oracle_sincos(double x, double *s, double *c);
+/* the PANOC engine of the restatement on the two unit-test problems of optimization_engine's mocks.rs
+ * (known answers mocks::SOLUTION_A / SOLUTION_HARD); which = 1 or 2, u has 2 or 3 entries */
+/* the L-BFGS restatement on a supplied history (known answer of the lbfgs crate's unit test); returns
+ * 100 * accepted updates + active pairs */
+int ttmpc_oracle_lbfgs_kat(int n, int mem, int n_updates, const double *g, const double *x, double *q,
+                           double *alpha0, double *rho0, int cbfgs);
+double ttmpc_oracle_lipschitz_mock(const double *u3);
+int ttmpc_oracle_panoc_mock(int which, double *u, double tolerance, int lbfgs_memory, int max_iter,
+                            int *iters, double *norm_fpr, long long *n_cost, long long *n_grad);
 int ttmpc_oracle_solve_batch_mode(const ttmpc_config *cfg, int n, const double *p,
                                   int use_u0, int use_y0, const double *c0,
                                   const ttmpc_result *res, int threads, int warp);

@@ -51,6 +51,12 @@ def load():
         lib.ttmpc_oracle_solve_batch_mode.argtypes = [CFG, I, VP, I, I, VP, C.POINTER(TtmpcResult), I, I]
         lib.ttmpc_oracle_eval_warp.argtypes = [CFG, VP, VP, D, VP, VP, VP, VP, VP]
         lib.ttmpc_oracle_sincos.argtypes = [D, C.POINTER(D), C.POINTER(D)]
+        lib.ttmpc_oracle_panoc_mock.argtypes = [I, VP, D, I, I, C.POINTER(C.c_int), C.POINTER(D), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        lib.ttmpc_oracle_panoc_mock.restype = I
+        lib.ttmpc_oracle_lbfgs_kat.argtypes = [I, I, I, VP, VP, VP, C.POINTER(D), C.POINTER(D), I]
+        lib.ttmpc_oracle_lbfgs_kat.restype = I
+        lib.ttmpc_oracle_lipschitz_mock.argtypes = [VP]
+        lib.ttmpc_oracle_lipschitz_mock.restype = D
         lib.ttdqn_oracle_observe_act.argtypes = [C.POINTER(TtdqnLayout), C.POINTER(TtdqnQnet), I] + [VP] * 12
         lib.ttdqn_oracle_observe.argtypes = [C.POINTER(TtdqnLayout), VP, VP, VP, VP, I, VP, VP]
         lib.ttdqn_oracle_project.argtypes = [VP, I, D, D]
@@ -110,6 +116,31 @@ def sincos(x):
     s = C.c_double(); c = C.c_double()
     lib.ttmpc_oracle_sincos(float(x), C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+def lbfgs_kat(mem, gs, xs, q, cbfgs=False):
+    """update_hessian(g_i, x_i) for every row, then apply_hessian(q) of the restated L-BFGS."""
+    lib = load()
+    gs = np.ascontiguousarray(gs, np.float64); xs = np.ascontiguousarray(xs, np.float64)
+    q = np.array(q, np.float64)
+    a = C.c_double(0.0); r = C.c_double(0.0)
+    code = lib.ttmpc_oracle_lbfgs_kat(gs.shape[1], int(mem), gs.shape[0], _p(gs), _p(xs), _p(q), C.byref(a), C.byref(r), int(cbfgs))
+    return dict(direction=q, alpha0=a.value, rho0=r.value, accepted=code // 100, active=code % 100)
+
+
+def lipschitz_mock(u3):
+    u = np.array(u3, np.float64)
+    return load().ttmpc_oracle_lipschitz_mock(_p(u))
+
+
+def panoc_mock(which, u0, tolerance, lbfgs_memory, max_iter):
+    """The restated PANOC engine on one of the two unit-test problems of optimization_engine's mocks.rs."""
+    lib = load()
+    u = np.array(u0, np.float64)
+    it = C.c_int(0); fpr = C.c_double(0.0); nc = C.c_longlong(0); ng = C.c_longlong(0)
+    st = lib.ttmpc_oracle_panoc_mock(int(which), _p(u), float(tolerance), int(lbfgs_memory), int(max_iter),
+                                     C.byref(it), C.byref(fpr), C.byref(nc), C.byref(ng))
+    return dict(u=u, exit_status=st, iterations=it.value, norm_fpr=fpr.value, cost_evals=nc.value, grad_evals=ng.value)
 
 
 def solve_batch(cfg, p, u0=None, y0=None, c0=None, threads=1, warp=False):

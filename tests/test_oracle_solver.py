@@ -1,6 +1,7 @@
 """CPU tests of the oracle's OpEn restatement (PANOC + ALM): properties the
 algorithm guarantees, determinism, and the two operation orders."""
 import numpy as np
+import pytest
 
 import trajtrack_mpcndqn_rlboost_b200 as t
 from tests import oracle_lib as O
@@ -116,3 +117,67 @@ def test_converged_solutions_are_local_minimisers_for_an_independent_optimizer(c
                      options=dict(maxiter=2000, ftol=1e-15, gtol=1e-10))
         assert f(u) - r.fun <= 5e-3 * max(1.0, abs(f(u))), (i, f(u), r.fun)
         assert np.abs(r.x - u).max() <= 0.1, (i, np.abs(r.x - u).max())
+
+
+# ------------------------------------------------------------------ known answers of the crate's own unit tests
+# optimization_engine's src/mocks.rs carries two small problems and the points its unit tests expect PANOC to reach
+# on them (panoc_engine.rs / panoc_optimizer.rs: `assert_nearly_equal_array(&u, &mocks::SOLUTION_A, ...)`).  The crate
+# is not in /root/reference (it is pulled by opengen==0.7.1), so problems and constants below are restated from it;
+# the test does not lean on that alone: the KKT conditions of the two problems are checked at the point reached.
+SOLUTION_A = np.array([-0.148_959_718_255_77, 0.133_457_867_273_39])                       # my_cost, ball of radius 0.2
+SOLUTION_HARD = np.array([-0.041_123_164_672_281, -0.028_440_417_469_206, 0.000_167_276_757_790])  # hard_quadratic, 0.05
+
+
+def _mock_grad(which, u):
+    if which == 1:
+        return np.array([u[0] + u[1] + 1.0, u[0] + 2.0 * u[1] - 1.0])
+    return np.array([4 * u[0] + 5 * u[1] + 25 * u[2] + 1, 5 * u[0] + 11 * u[1] + 5 * u[2] + 1,
+                     25 * u[0] + 5 * u[1] + 1001 * u[2] + 1])
+
+
+@pytest.mark.parametrize("which,u0,radius,expected,mem", [(1, [0.0, 0.0], 0.2, SOLUTION_A, 2),
+                                                          (2, [-20.0, 10.0, 0.2], 0.05, SOLUTION_HARD, 3)])
+def test_panoc_engine_reaches_the_known_answers_of_the_crates_unit_tests(which, u0, radius, expected, mem):
+    r = O.panoc_mock(which, u0, tolerance=1e-10, lbfgs_memory=mem, max_iter=1000)
+    assert r["exit_status"] == 0 and r["norm_fpr"] < 1e-10 and r["iterations"] < 100
+    u = r["u"]
+    assert np.abs(u - expected).max() < 1e-9
+    # KKT on the ball (the unconstrained minimisers lie outside): |u| = r and the gradient points along -u
+    g = _mock_grad(which, u)
+    assert abs(np.linalg.norm(u) - radius) < 1e-12
+    assert np.linalg.norm(g + np.linalg.norm(g) * u / radius) < 1e-8 * np.linalg.norm(g)
+    # the recalled constants satisfy the same conditions (to their 14 printed digits)
+    ge = _mock_grad(which, expected)
+    assert abs(np.linalg.norm(expected) - radius) < 1e-12
+    assert np.linalg.norm(ge + np.linalg.norm(ge) * expected / radius) < 1e-10 * np.linalg.norm(ge)
+
+
+def test_panoc_engine_on_the_crates_basic_test_settings():
+    """t_panoc_basic of the crate: tolerance 1e-4, L-BFGS memory 2, start at the origin, the answer within 1e-4."""
+    r = O.panoc_mock(1, [0.0, 0.0], tolerance=1e-4, lbfgs_memory=2, max_iter=10)
+    assert r["exit_status"] == 0 and r["iterations"] < 10 and r["norm_fpr"] < 1e-4
+    assert np.abs(r["u"] - SOLUTION_A).max() < 1e-4
+
+
+def test_lbfgs_restatement_against_the_known_answer_of_the_lbfgs_crate():
+    """`correctneess_buff_1` of the lbfgs crate (the one PANOCCache uses): after update_hessian(0, 0) and
+    update_hessian([-0.5, 0.6, -1.2], [0.1, 0.2, -0.3]) apply_hessian turns [-3.1, 1.5, 2.1] into the direction
+    below, with alpha = -1.488..., rho = 2.325...  Constants restated from the crate's test; rho = 1 / 0.43 and
+    alpha = rho * (-0.64) can be checked by hand."""
+    gs = [[0.0, 0.0, 0.0], [-0.5, 0.6, -1.2]]
+    xs = [[0.0, 0.0, 0.0], [0.1, 0.2, -0.3]]
+    for cbfgs in (False, True):   # Lbfgs::new defaults, and the C-BFGS settings PANOCCache::new chooses
+        r = O.lbfgs_kat(3, gs, xs, [-3.1, 1.5, 2.1], cbfgs=cbfgs)
+        assert r["active"] == 1
+        assert np.allclose(r["direction"], [-1.100601247872944, -0.086568349404424, 0.948633011911515], rtol=0, atol=1e-14)
+        assert abs(r["alpha0"] - (-1.488372093023256)) < 1e-14 and abs(r["rho0"] - 2.325581395348837) < 1e-14
+    # a pair with y's <= sy_epsilon is rejected and leaves the buffer as it was (update_hessian -> UpdateStatus::Rejection)
+    r = O.lbfgs_kat(3, gs + [[-0.5, 0.6, -1.2]], xs + [[0.2, 0.1, -0.3]], [-3.1, 1.5, 2.1])
+    assert r["active"] == 1 and np.allclose(r["direction"], [-1.100601247872944, -0.086568349404424, 0.948633011911515], atol=1e-14)
+
+
+def test_lipschitz_estimate_against_the_crates_mock():
+    """t_test_lip_estimator_mock of the crate: gradient (3 u0, 2 u1, 4.5) at (1, 2, 3) -> 1.336306209562 = 5 / sqrt(14)
+    (the probe step h_i = max(delta, epsilon u_i) is proportional to u here, so PANOC's delta / epsilon give the same)."""
+    L = O.lipschitz_mock([1.0, 2.0, 3.0])
+    assert abs(L - 1.336306209562) < 1e-8 and abs(L - 5.0 / np.sqrt(14.0)) < 1e-8
